@@ -1,0 +1,126 @@
+/* b200remap.h -- C ABI of libb200remap.so: pyremap's weight-application hot path
+ * on NVIDIA B200 (sm_100a).
+ *
+ * pyremap (reference tree /root/reference, v2.4.0) has no FFI layer of its own:
+ * the native code its hot path executes is scipy's
+ *     csr_matvecs(n_row, n_col, n_vecs, Ap, Aj, Ax, Xx, Yx)
+ * reached from `matrix.dot(...)` at pyremap/remapper/remap_numpy.py:264,265,268,
+ * wrapped by ~10 NumPy passes (remap_numpy.py:256-278).  The entry points below are
+ * what a ctypes binding inside pyremap/remapper/remap_numpy.py would bind to replace
+ * exactly that (see INTEGRATION.md for the stub):
+ *
+ *   b200remap_csr_create   <- scipy.sparse.csr_matrix(...) result of _load_mapping,
+ *                             remap_numpy.py:134-137 (+ frac_b read at :270)
+ *   b200remap_spmm         <- matrix.dot(...) x1 or x2 plus remap_numpy.py:258-278
+ *                             (mask product, threshold, divide, NaN fill), fused
+ *   b200remap_any_nan      <- np.isnan(field) / np.count_nonzero(mask) > 0,
+ *                             remap_numpy.py:202-204 (branch selection)
+ *   b200remap_transpose    <- in_field.transpose(...).reshape(...) / np.transpose,
+ *                             remap_numpy.py:256 and :295 (layout only)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no exceptions or aborts cross the boundary.
+ *   - return value 0 = success; < 0 = library error (B200REMAP_E_*); > 0 = cudaError_t.
+ *     b200remap_last_error() returns a thread-local description of the last failure.
+ *   - X / Y / flags are caller-owned DEVICE pointers on the handle's device; launches
+ *     are asynchronous on `cuda_stream` (a cudaStream_t / CUstream, NULL = default).
+ *   - a handle is immutable after create: concurrent calls on different streams are safe.
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry fails.
+ */
+#ifndef B200REMAP_H_
+#define B200REMAP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REMAP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define B200REMAP_API __attribute__((visibility("default")))
+#else
+#define B200REMAP_API
+#endif
+
+/* library error codes (negative) */
+#define B200REMAP_E_INVALID   (-1)  /* bad argument (null, negative size, misaligned, ...) */
+#define B200REMAP_E_UNSUPPORTED (-2) /* valid request this build cannot serve */
+#define B200REMAP_E_NODEVICE  (-3)  /* no CUDA device / wrong architecture */
+#define B200REMAP_E_NOMEM     (-4)  /* host allocation failed */
+
+/* element type of the field X (the output Y is always float64, like the reference,
+ * whose S is float64: remap_numpy.py:136) */
+#define B200REMAP_F64 0
+#define B200REMAP_F32 1
+
+/* what b200remap_spmm computes per output element (i = destination row, k = column) */
+#define B200REMAP_MODE_RAW    0  /* Y = S@X                                   (csr_matvecs) */
+#define B200REMAP_MODE_FRACB  1  /* unmasked branch, remap_numpy.py:268-278:
+                                    Y = frac_b[i] > 0 ? (S@X)/frac_b[i] : NaN            */
+#define B200REMAP_MODE_MASKED 2  /* masked branch, remap_numpy.py:263-266,277-278:
+                                    v = valid(x); num = S@(v ? x : 0.0); den = S@(v ? 1.0 : 0.0)
+                                    Y = den > threshold ? num/den : NaN
+                                    valid(x) = explicit byte mask if given, else !isnan(x) */
+
+/* kernel selection (0 = let the library choose from K and the row-length profile) */
+#define B200REMAP_KERNEL_AUTO     0
+#define B200REMAP_KERNEL_LANES_K  1  /* lanes across K, one thread per (row, K-chunk)   */
+#define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums */
+
+typedef struct b200remap_csr b200remap_csr;
+
+B200REMAP_API int b200remap_abi_version(void);
+B200REMAP_API const char *b200remap_last_error(void);
+
+/* number of visible CUDA devices and compute capability (major*10+minor) of `device` */
+B200REMAP_API int b200remap_device_count(int *count);
+B200REMAP_API int b200remap_device_arch(int device, int *sm);
+
+/* Build the library-owned device copy of a CSR weight matrix in scipy's canonical form
+ * (rows = destination cells, column indices sorted within a row, no duplicates), plus
+ * the optional destination fraction `frac_b` [n_row] (required for MODE_FRACB).
+ * Input pointers are HOST pointers unless ptrs_are_device != 0. */
+B200REMAP_API int b200remap_csr_create(int device, int64_t n_row, int64_t n_col, int64_t nnz,
+                         const int32_t *indptr, const int32_t *indices,
+                         const double *data, const double *frac_b,
+                         int ptrs_are_device, b200remap_csr **out);
+B200REMAP_API void b200remap_csr_destroy(b200remap_csr *csr);
+
+/* info[0..7] = n_row, n_col, nnz, n_touched (distinct source rows referenced),
+ *              max nnz per row, number of empty rows, device, has_frac_b */
+B200REMAP_API int b200remap_csr_info(const b200remap_csr *csr, int64_t info[8]);
+
+/* Y[b] = remap(S, X[b]) for b in [0, nbatch):
+ *   X[b] = X + b*x_batch_stride, row-major [n_col, K] with leading dimension ldx (elements)
+ *   Y[b] = Y + b*y_batch_stride, row-major [n_row, K] with leading dimension ldy, float64
+ *   valid    (nullable) explicit validity bytes laid out exactly like X (MODE_MASKED only)
+ *   keep_out (nullable) receives the keep flag of every output element, laid out like Y
+ * Per row the stored entries are accumulated in stored order with a separately rounded
+ * multiply and add starting from +0.0, i.e. bit-for-bit scipy's csr_matvecs. */
+B200REMAP_API int b200remap_spmm(const b200remap_csr *csr, const void *X, int x_dtype, int64_t K,
+                   int64_t ldx, int64_t nbatch, int64_t x_batch_stride,
+                   const uint8_t *valid, double *Y, int64_t ldy,
+                   int64_t y_batch_stride, uint8_t *keep_out, int mode,
+                   double threshold, int kernel, void *cuda_stream);
+
+/* *flag_dev (device int32) := 1 if any of the n elements of X is NaN, else 0.
+ * Blocks stop reading as soon as a NaN has been seen anywhere. */
+B200REMAP_API int b200remap_any_nan(const void *X, int x_dtype, int64_t n, int32_t *flag_dev,
+                      void *cuda_stream);
+
+/* out[b][c][r] = in[b][r][c]  (batched 2-D transpose; rows x cols -> cols x rows),
+ * used for field-major layouts either side of the product.  elem_size is 4 or 8. */
+B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
+                        int64_t rows, int64_t cols, void *cuda_stream);
+
+/* tuning knobs for experiments (process-wide; 0 restores the default):
+ *   0: threads per CTA of the LANES_K kernel   1: load cache policy (0 default,1 L1 no-allocate,2 L1 evict-last)
+ *   2: nonzeros in flight per lane (2,4,8)     3: force vector width (1,2,4)            */
+B200REMAP_API int b200remap_set_tunable(int which, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REMAP_H_ */

@@ -1,0 +1,181 @@
+"""ctypes binding of ``libb200remap.so`` (the C ABI declared in ``include/b200remap.h``).
+
+There is deliberately no fallback: if the shared object cannot be built or
+loaded, or no sm_100 device is present, every compute entry raises
+:class:`B200RemapError`.  PyTorch tensors are used only as device-buffer carriers
+(``data_ptr()``) and for the current CUDA stream.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK = 0, 1, 2
+F64, F32 = 0, 1
+
+#: every symbol ``include/b200remap.h`` declares
+EXPORTED_SYMBOLS = (
+    'b200remap_abi_version', 'b200remap_last_error', 'b200remap_device_count',
+    'b200remap_device_arch', 'b200remap_csr_create', 'b200remap_csr_destroy',
+    'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
+    'b200remap_transpose', 'b200remap_set_tunable',
+)
+
+
+class B200RemapError(RuntimeError):
+    """A call into libb200remap failed (``code`` < 0: library, > 0: cudaError_t)."""
+
+    def __init__(self, code, message):
+        super().__init__(f'libb200remap error {code}: {message}')
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load_library():
+    """Load (building first if the sources are newer) the CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            try:
+                _build.build_library()
+            except Exception as exc:
+                if not os.path.exists(path):
+                    raise B200RemapError(
+                        -3, f'{path} is missing and could not be built ({exc}); '
+                        'pyremap_b200 has no CPU fallback') from exc
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as exc:
+            raise B200RemapError(
+                -3, f'cannot load {path}: {exc}; pyremap_b200 has no CPU '
+                'fallback') from exc
+        i32, i64, dbl, vp = (ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+                             ctypes.c_void_p)
+        lib.b200remap_abi_version.argtypes = []
+        lib.b200remap_abi_version.restype = i32
+        lib.b200remap_last_error.argtypes = []
+        lib.b200remap_last_error.restype = ctypes.c_char_p
+        lib.b200remap_device_count.argtypes = [ctypes.POINTER(i32)]
+        lib.b200remap_device_arch.argtypes = [i32, ctypes.POINTER(i32)]
+        lib.b200remap_csr_create.argtypes = [i32, i64, i64, i64, vp, vp, vp, vp,
+                                             i32, ctypes.POINTER(vp)]
+        lib.b200remap_csr_destroy.argtypes = [vp]
+        lib.b200remap_csr_destroy.restype = None
+        lib.b200remap_csr_info.argtypes = [vp, ctypes.POINTER(i64)]
+        lib.b200remap_spmm.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp,
+                                       i64, i64, vp, i32, dbl, i32, vp]
+        lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
+        lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+        lib.b200remap_set_tunable.argtypes = [i32, i32]
+        for name in ('b200remap_device_count', 'b200remap_device_arch',
+                     'b200remap_csr_create', 'b200remap_csr_info',
+                     'b200remap_spmm', 'b200remap_any_nan',
+                     'b200remap_transpose', 'b200remap_set_tunable'):
+            getattr(lib, name).restype = i32
+        if lib.b200remap_abi_version() != 1:
+            raise B200RemapError(-2, 'ABI version mismatch')
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        msg = load_library().b200remap_last_error()
+        raise B200RemapError(code, msg.decode('utf-8', 'replace') if msg else '')
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    code = load_library().b200remap_device_count(ctypes.byref(n))
+    return n.value if code == 0 else 0
+
+
+def set_tunable(which, value):
+    check(load_library().b200remap_set_tunable(int(which), int(value)))
+
+
+def _np_ptr(arr):
+    return None if arr is None else ctypes.c_void_p(arr.ctypes.data)
+
+
+class DeviceCSR:
+    """Owner of one ``b200remap_csr`` handle (device copy of the weight matrix)."""
+
+    def __init__(self, indptr, indices, data, frac_b, n_col, device=0):
+        import numpy as np
+        lib = load_library()
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        if frac_b is not None:
+            frac_b = np.ascontiguousarray(frac_b, dtype=np.float64)
+            if frac_b.size != indptr.size - 1:
+                raise ValueError('frac_b must have one entry per destination row')
+        handle = ctypes.c_void_p()
+        check(lib.b200remap_csr_create(
+            int(device), indptr.size - 1, int(n_col), data.size, _np_ptr(indptr),
+            _np_ptr(indices), _np_ptr(data), _np_ptr(frac_b), 0,
+            ctypes.byref(handle)))
+        self._handle = handle
+        self._lib = lib
+        info = (ctypes.c_int64 * 8)()
+        check(lib.b200remap_csr_info(handle, info))
+        (self.n_row, self.n_col, self.nnz, self.n_touched, self.max_row_nnz,
+         self.n_empty_rows, self.device, has_frac) = [int(v) for v in info]
+        self.has_frac_b = bool(has_frac)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            self._lib.b200remap_csr_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def spmm(self, x_ptr, x_dtype, K, ldx, nbatch, x_batch_stride, y_ptr, ldy,
+             y_batch_stride, mode, threshold=0.0, valid_ptr=None,
+             keep_ptr=None, kernel=KERNEL_AUTO, stream=0):
+        """Raw pointer-level call of ``b200remap_spmm`` (asynchronous)."""
+        if not self._handle:
+            raise B200RemapError(-1, 'DeviceCSR is closed')
+        check(self._lib.b200remap_spmm(
+            self._handle, ctypes.c_void_p(x_ptr), int(x_dtype), int(K), int(ldx),
+            int(nbatch), int(x_batch_stride),
+            ctypes.c_void_p(valid_ptr) if valid_ptr else None,
+            ctypes.c_void_p(y_ptr), int(ldy), int(y_batch_stride),
+            ctypes.c_void_p(keep_ptr) if keep_ptr else None, int(mode),
+            float(threshold), int(kernel),
+            ctypes.c_void_p(stream) if stream else None))
+
+
+def any_nan(x_ptr, x_dtype, n, flag_ptr, stream=0):
+    check(load_library().b200remap_any_nan(
+        ctypes.c_void_p(x_ptr), int(x_dtype), int(n), ctypes.c_void_p(flag_ptr),
+        ctypes.c_void_p(stream) if stream else None))
+
+
+def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0):
+    check(load_library().b200remap_transpose(
+        ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), int(elem_size),
+        int(nbatch), int(rows), int(cols),
+        ctypes.c_void_p(stream) if stream else None))

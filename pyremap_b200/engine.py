@@ -1,0 +1,251 @@
+"""Array-level weight application on the GPU: the body of the reference's
+``_remap_numpy_array`` (``/root/reference/pyremap/remapper/remap_numpy.py:223-297``)
+expressed as one fused kernel launch through the C ABI.
+
+Layout.  The reference permutes the field so the source (remap) axes come first,
+flattens to ``[nSrc, K]`` (a full copy, ``:256``), multiplies, and permutes back
+(``:280-295``).  When the remap axes are adjacent and in order -- every field
+pyremap's own callers produce -- the field already *is* ``[B, nSrc, L]`` in memory
+(``B`` = leading extra dims, ``L`` = trailing extra dims), and the wanted output
+``[B, nDst, L]`` is exactly what a batched launch writes: no copy on either side.
+Only ``L == 1`` with ``B > 1`` (source dims last, e.g. ``(time, lat, lon)``) is
+transposed on the device so that K is contiguous for the gather.
+
+PyTorch is used as the device-buffer carrier and for H2D/D2H copies only.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import (F32, F64, KERNEL_AUTO, MODE_FRACB, MODE_MASKED, MODE_RAW,
+                    B200RemapError)
+
+_MAX_BATCH = 65535
+
+
+def _torch():
+    try:
+        import torch
+    except ImportError as exc:  # pragma: no cover
+        raise B200RemapError(-3, 'PyTorch is required as the device-tensor '
+                             'carrier') from exc
+    return torch
+
+
+def require_cuda(device=None):
+    """Resolve the CUDA device to run on; fail loudly when there is none."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise B200RemapError(
+            -3, 'no CUDA device is available; pyremap_b200 runs on NVIDIA B200 '
+            '(sm_100a) only and has no CPU fallback')
+    if device is None:
+        return torch.device('cuda', torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise B200RemapError(-1, f'device must be a CUDA device, got {device}')
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    return device
+
+
+class Layout:
+    """How a field of ``shape`` with ``remap_axes`` maps onto ``[B, nSrc, L]``."""
+
+    def __init__(self, shape, remap_axes, dst_dims):
+        shape = tuple(int(s) for s in shape)
+        remap_axes = [int(a) for a in remap_axes]
+        if len(set(remap_axes)) != len(remap_axes) or not remap_axes:
+            raise ValueError(f'invalid remap_axes {remap_axes}')
+        for a in remap_axes:
+            if a < 0 or a >= len(shape):
+                raise ValueError(f'remap axis {a} out of range for {len(shape)}-d field')
+        self.shape = shape
+        self.remap_axes = remap_axes
+        self.extra_axes = [a for a in range(len(shape)) if a not in remap_axes]
+        self.extra_shape = [shape[a] for a in self.extra_axes]
+        self.dst_dims = [int(d) for d in dst_dims]
+        self.n_src = int(np.prod([shape[a] for a in remap_axes], dtype=np.int64))
+        self.n_dst = int(np.prod(self.dst_dims, dtype=np.int64))
+        self.K = int(np.prod(self.extra_shape, dtype=np.int64)) if self.extra_axes else 1
+        first = min(remap_axes)
+        self.first = first
+        self.adjacent = remap_axes == list(range(first, first + len(remap_axes)))
+        if self.adjacent:
+            self.B = int(np.prod(shape[:first], dtype=np.int64)) if first else 1
+            self.L = int(np.prod(shape[first + len(remap_axes):], dtype=np.int64))
+            self.out_shape = shape[:first] + tuple(self.dst_dims) + shape[first + len(remap_axes):]
+        else:
+            self.B, self.L = 1, self.K
+            lead = [shape[a] for a in self.extra_axes[:first]]
+            tail = [shape[a] for a in self.extra_axes[first:]]
+            self.out_shape = tuple(lead) + tuple(self.dst_dims) + tuple(tail)
+
+    def unpermute_axes(self):
+        """Axes order that moves ``dst_dims + extra`` back (remap_numpy.py:288-295)."""
+        n_dst = len(self.dst_dims)
+        tail = list(range(n_dst, n_dst + len(self.extra_shape)))
+        return tail[:self.first] + list(range(n_dst)) + tail[self.first:]
+
+
+def _as_device_tensor(array, device, torch):
+    """numpy / torch (any device) -> contiguous f32/f64 CUDA tensor on ``device``."""
+    if isinstance(array, torch.Tensor):
+        t = array
+        if t.dtype not in (torch.float64, torch.float32):
+            t = t.to(torch.float64)
+        return t.to(device, non_blocking=True)
+    a = np.asarray(array)
+    if a.dtype not in (np.float64, np.float32):
+        # ints / float16 / bool: the reference upcasts through the float64 weights
+        a = a.astype(np.float64)
+    if not a.dtype.isnative:
+        a = a.astype(a.dtype.newbyteorder('='))
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
+    t = torch.from_numpy(a)
+    return t.to(device, non_blocking=True)
+
+
+def _dtype_code(t, torch):
+    return F64 if t.dtype == torch.float64 else F32
+
+
+def device_any_nan(x, stream=None):
+    """True iff the CUDA tensor ``x`` contains a NaN (kernel K4, early exit)."""
+    torch = _torch()
+    x = x if x.is_contiguous() else x.contiguous()
+    with torch.cuda.device(x.device):
+        flag = torch.empty(1, dtype=torch.int32, device=x.device)
+        st = (stream or torch.cuda.current_stream(x.device)).cuda_stream
+        _cabi.any_nan(x.data_ptr(), _dtype_code(x, torch), x.numel(),
+                      flag.data_ptr(), st)
+        return bool(flag.item())
+
+
+def _transpose2d(t, nbatch, rows, cols, torch):
+    """[nbatch, rows, cols] -> [nbatch, cols, rows] through kernel K5."""
+    out = torch.empty((nbatch, cols, rows), dtype=t.dtype, device=t.device)
+    _cabi.transpose(t.data_ptr(), out.data_ptr(), t.element_size(), nbatch, rows,
+                    cols, torch.cuda.current_stream(t.device).cuda_stream)
+    return out
+
+
+def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
+                  valid=None, mode='auto', device=None, want_keep=False,
+                  return_torch=False, kernel=KERNEL_AUTO):
+    """Remap ``field`` and return the NaN-filled float64 result.
+
+    Parameters
+    ----------
+    matrix : pyremap_b200.mapfile.WeightMatrix
+    dst_dims : destination grid dims in C order (``dst_grid_dims[::-1]``)
+    field : numpy array or torch tensor (host or CUDA), any numeric dtype
+    remap_axes : positions of the source dims in ``field``
+    threshold : renormalisation threshold or None
+    valid : optional boolean array shaped like ``field`` (True = use the value);
+        selects the masked branch with an explicit mask (a ``MaskedArray``'s
+        ``~mask``).  Without it the masked branch derives validity from
+        ``!isnan``, as ``_remap_data_array`` does (remap_numpy.py:202-204).
+    mode : 'auto' | 'raw' | 'fracb' | 'masked'.  'auto' reproduces the
+        reference's branch selection: masked iff a threshold is given and the
+        field has a mask (explicit, or any NaN anywhere), else ``frac_b``.
+    want_keep : also return the boolean keep mask (``~`` of the reference's
+        output mask).
+
+    Returns ``out`` or ``(out, keep)``; numpy arrays unless ``return_torch``.
+    """
+    torch = _torch()
+    device = require_cuda(device if device is not None else (
+        field.device if isinstance(field, torch.Tensor) and field.is_cuda else None))
+    lay = Layout(field.shape, remap_axes, dst_dims)
+    if lay.n_src != matrix.shape[1]:
+        raise ValueError(f'field has {lay.n_src} source cells but the map has '
+                         f'{matrix.shape[1]}')
+    if lay.n_dst != matrix.shape[0]:
+        raise ValueError(f'destination dims {lay.dst_dims} do not match the map '
+                         f'({matrix.shape[0]} rows)')
+    csr = matrix.on_device(device.index)
+
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device)
+        x = _as_device_tensor(field, device, torch)
+        v = None
+        if valid is not None:
+            vv = valid if isinstance(valid, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(np.asarray(valid, dtype=np.uint8)))
+            v = vv.to(device=device, dtype=torch.uint8, non_blocking=True)
+            if tuple(v.shape) != tuple(x.shape):
+                raise ValueError('valid must have the same shape as field')
+
+        # ---- branch selection (remap_numpy.py:202-204, 258-261) ----
+        if mode == 'auto':
+            if threshold is None:
+                mode_code = MODE_FRACB
+            elif v is not None:
+                mode_code = MODE_MASKED
+            else:
+                mode_code = MODE_MASKED if device_any_nan(x, stream) else MODE_FRACB
+        else:
+            mode_code = {'raw': MODE_RAW, 'fracb': MODE_FRACB,
+                         'masked': MODE_MASKED}[mode]
+        if mode_code == MODE_MASKED and threshold is None:
+            raise ValueError('the masked branch needs a renormalization threshold')
+        if mode_code != MODE_MASKED:
+            v = None
+        if mode_code == MODE_FRACB and not csr.has_frac_b:
+            raise ValueError('the map has no frac_b; cannot take the unmasked branch')
+        thr = float(threshold) if threshold is not None else 0.0
+
+        # ---- bring the field to [B, nSrc, L] with L contiguous ----
+        transposed = False
+        if lay.adjacent:
+            B, L = lay.B, lay.L
+            x3 = x.contiguous().view(B, lay.n_src, L)
+            v3 = None if v is None else v.contiguous().view(B, lay.n_src, L)
+            if L == 1 and B > 1:
+                # source dims last: make the batch the contiguous K axis
+                x3 = _transpose2d(x3, 1, B, lay.n_src, torch).view(1, lay.n_src, B)
+                if v3 is not None:
+                    v3 = v3.view(B, lay.n_src).t().contiguous().view(1, lay.n_src, B)
+                transposed, B, L = True, 1, lay.B
+        else:
+            order = lay.remap_axes + lay.extra_axes
+            x3 = x.permute(order).reshape(1, lay.n_src, lay.K).contiguous()
+            v3 = None if v is None else v.permute(order).reshape(
+                1, lay.n_src, lay.K).contiguous()
+            B, L = 1, lay.K
+
+        y3 = torch.empty((B, lay.n_dst, L), dtype=torch.float64, device=device)
+        k3 = torch.empty((B, lay.n_dst, L), dtype=torch.uint8,
+                         device=device) if want_keep else None
+        if L > 0 and lay.n_dst > 0:
+            for b0 in range(0, B, _MAX_BATCH):
+                nb = min(_MAX_BATCH, B - b0)
+                csr.spmm(x3[b0].data_ptr(), _dtype_code(x3, torch), L, L, nb,
+                         lay.n_src * L, y3[b0].data_ptr(), L, lay.n_dst * L,
+                         mode_code, thr,
+                         valid_ptr=None if v3 is None else v3[b0].data_ptr(),
+                         keep_ptr=None if k3 is None else k3[b0].data_ptr(),
+                         kernel=kernel, stream=stream.cuda_stream)
+
+        # ---- back to the caller's layout (remap_numpy.py:280-295) ----
+        def restore(t3):
+            if lay.adjacent:
+                if transposed:
+                    t3 = _transpose2d(t3.view(1, lay.n_dst, lay.B), 1, lay.n_dst,
+                                      lay.B, torch) if t3.dtype != torch.uint8 else \
+                        t3.view(lay.n_dst, lay.B).t().contiguous()
+                return t3.reshape(lay.out_shape)
+            full = t3.reshape(lay.dst_dims + lay.extra_shape)
+            return full.permute(lay.unpermute_axes()).contiguous()
+
+        out = restore(y3)
+        keep = restore(k3).to(torch.bool) if want_keep else None
+        if not return_torch:
+            out = out.cpu().numpy()
+            keep = None if keep is None else keep.cpu().numpy()
+    return (out, keep) if want_keep else out

@@ -1,0 +1,194 @@
+"""Mapping-file loading: SCRIP/ESMF weights -> row-sorted canonical CSR on the host.
+
+Mirrors the one-time part of the reference's ``_load_mapping``
+(``/root/reference/pyremap/remapper/remap_numpy.py:72-139``): read ``n_a``, ``n_b``,
+``S``, ``row``, ``col`` (1-based), ``frac_b``, ``src_grid_dims``, ``dst_grid_dims``
+and build the matrix ``csr_matrix((S, (row-1, col-1)), shape=(n_b, n_a))``
+(``:134-137``) -- i.e. rows = destination cells, columns sorted within a row,
+duplicate ``(row, col)`` entries summed.  The CSR builder here is our own (NumPy);
+it does not call scipy.
+
+Readers: real xarray if importable (any NetCDF flavour it supports), ``.npz``
+(synthetic maps of this repo), NetCDF-3 via ``scipy.io.netcdf_file``, NetCDF-4
+via ``netCDF4``/``h5py`` when present.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+class _Var:
+    """Minimal variable view (``.values``) so ``remapper._ds_map['frac_b'].values``
+    keeps working when xarray is not installed (reference remap_numpy.py:252,270)."""
+
+    def __init__(self, values):
+        self.values = values
+
+
+class MapDataset:
+    """Dictionary-backed stand-in for the opened map ``xr.Dataset``."""
+
+    def __init__(self, variables, sizes):
+        self._vars = {k: _Var(v) for k, v in variables.items()}
+        self.sizes = dict(sizes)
+
+    def __getitem__(self, key):
+        return self._vars[key]
+
+    def __contains__(self, key):
+        return key in self._vars
+
+    def close(self):
+        pass
+
+
+_NEEDED = ('S', 'row', 'col', 'frac_b', 'src_grid_dims', 'dst_grid_dims')
+
+
+def _from_arrays(get):
+    arrays = {k: np.asarray(get(k)) for k in _NEEDED}
+    sizes = {
+        'n_s': arrays['S'].size,
+        'n_b': arrays['frac_b'].size,
+        'src_grid_rank': arrays['src_grid_dims'].size,
+        'dst_grid_rank': arrays['dst_grid_dims'].size,
+    }
+    return arrays, sizes
+
+
+def open_map(filename):
+    """Open a mapping file; returns an object offering ``ds['S'].values`` and
+    ``ds.sizes['n_a']`` (an ``xr.Dataset`` when xarray is installed)."""
+    filename = str(filename)
+    if filename.endswith('.npz'):
+        with np.load(filename, allow_pickle=False) as npz:
+            arrays, sizes = _from_arrays(lambda k: npz[k])
+            if 'frac_a' in npz.files:
+                sizes['n_a'] = int(npz['frac_a'].size)
+            elif 'n_a' in npz.files:
+                sizes['n_a'] = int(npz['n_a'])
+            else:
+                sizes['n_a'] = int(np.prod(arrays['src_grid_dims']))
+        return MapDataset(arrays, sizes)
+    try:
+        import xarray as xr
+        if hasattr(xr, 'open_dataset'):
+            return xr.open_dataset(filename)
+    except ImportError:
+        pass
+    with open(filename, 'rb') as fh:
+        magic = fh.read(4)
+    if magic[:3] == b'CDF':
+        from scipy.io import netcdf_file
+        with netcdf_file(filename, 'r', mmap=False) as nc:
+            arrays, sizes = _from_arrays(lambda k: np.array(nc.variables[k][...]))
+            sizes['n_a'] = int(nc.dimensions['n_a'])
+        return MapDataset(arrays, sizes)
+    try:
+        import netCDF4
+        with netCDF4.Dataset(filename) as nc:
+            arrays, sizes = _from_arrays(lambda k: np.array(nc.variables[k][...]))
+            sizes['n_a'] = int(nc.dimensions['n_a'].size)
+        return MapDataset(arrays, sizes)
+    except ImportError:
+        pass
+    try:
+        import h5py
+        with h5py.File(filename, 'r') as h5:
+            arrays, sizes = _from_arrays(lambda k: np.array(h5[k]))
+            sizes['n_a'] = int(h5['n_a'].shape[0]) if 'n_a' in h5 else int(
+                np.prod(arrays['src_grid_dims']))
+        return MapDataset(arrays, sizes)
+    except ImportError:
+        pass
+    raise OSError(
+        f'cannot read {filename}: it is NetCDF-4/HDF5 and none of xarray, '
+        'netCDF4 or h5py is installed')
+
+
+def coo_to_csr(S, row0, col0, n_row, n_col):
+    """Canonical CSR (sorted columns, duplicates summed) from 0-based triplets.
+
+    Same result as ``scipy.sparse.csr_matrix((S, (row, col)))`` used by the
+    reference (remap_numpy.py:137): entries are ordered by (row, col) with a
+    *stable* sort and equal (row, col) pairs are added left to right in file
+    order.  (scipy's in-row sort is std::sort; for three or more duplicates of
+    one (row, col) in a row longer than 16 its addition order is unspecified, so
+    bit-equality with scipy is guaranteed for up to two duplicates per pair --
+    map files written by ESMF/MOAB contain none.)
+    """
+    S = np.asarray(S, dtype=np.float64).ravel()
+    row0 = np.asarray(row0).ravel()
+    col0 = np.asarray(col0).ravel()
+    if not (S.size == row0.size == col0.size):
+        raise ValueError('S, row and col must have the same length')
+    n_row, n_col = int(n_row), int(n_col)
+    if S.size:
+        if row0.min() < 0 or row0.max() >= n_row:
+            raise ValueError('row index out of range for n_b')
+        if col0.min() < 0 or col0.max() >= n_col:
+            raise ValueError('col index out of range for n_a')
+    if S.size >= 2**31 - 1 or n_row >= 2**31 - 1 or n_col >= 2**31 - 1:
+        raise ValueError('int32 CSR only: sizes must be below 2**31')
+    key = row0.astype(np.int64) * n_col + col0.astype(np.int64)
+    if S.size > 1:
+        step = np.diff(key)
+        if not np.all(step > 0):                       # not already canonical
+            order = np.argsort(key, kind='stable')
+            key = key[order]
+            S = S[order]
+            dup = np.concatenate([[False], np.diff(key) == 0])
+            if dup.any():
+                starts = np.nonzero(~dup)[0]
+                # left-to-right sums within each run of equal keys
+                summed = S[starts].copy()
+                run = np.cumsum(~dup) - 1
+                for j in np.nonzero(dup)[0]:
+                    summed[run[j]] = summed[run[j]] + S[j]
+                S = summed
+                key = key[starts]
+    rows = (key // n_col).astype(np.int64)
+    indices = (key - rows * n_col).astype(np.int32)
+    counts = np.bincount(rows, minlength=n_row)
+    indptr = np.zeros(n_row + 1, dtype=np.int32)
+    np.cumsum(counts, out=indptr[1:])
+    return indptr, indices, np.ascontiguousarray(S, dtype=np.float64)
+
+
+class WeightMatrix:
+    """Host-side canonical CSR of the map plus lazily created device copies.
+
+    Takes the place of ``remapper._matrix`` (a ``scipy.sparse.csr_matrix`` in the
+    reference, remap_numpy.py:137).  ``shape``, ``nnz``, ``indptr``, ``indices``,
+    ``data`` are spelled like scipy's so diagnostics keep working; ``dot`` is
+    intentionally absent -- products run on the GPU only.
+    """
+
+    def __init__(self, indptr, indices, data, shape, frac_b=None):
+        self.indptr = indptr
+        self.indices = indices
+        self.data = data
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.frac_b = None if frac_b is None else np.ascontiguousarray(
+            frac_b, dtype=np.float64)
+        self._device = {}
+
+    @property
+    def nnz(self):
+        return int(self.data.size)
+
+    def on_device(self, device=0):
+        """The ``DeviceCSR`` handle for CUDA device ``device`` (created once)."""
+        from ._cabi import DeviceCSR
+        device = int(device)
+        if device not in self._device:
+            self._device[device] = DeviceCSR(self.indptr, self.indices,
+                                             self.data, self.frac_b,
+                                             self.shape[1], device)
+        return self._device[device]
+
+    def release(self):
+        for h in self._device.values():
+            h.close()
+        self._device = {}

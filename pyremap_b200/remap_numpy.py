@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's in-memory remap module, with the array
+arithmetic moved to the GPU.
+
+Function names, arguments, error messages and return types follow
+``/root/reference/pyremap/remapper/remap_numpy.py`` one to one so that the
+reference's tests (and callers such as MPAS-Analysis) read the same:
+
+=====================  =======================  ================================
+here                   reference                what changed
+=====================  =======================  ================================
+``_remap_numpy``       remap_numpy.py:19-69     nothing (xarray plumbing)
+``_load_mapping``      remap_numpy.py:72-139    CSR built by us, kept on host and
+                                                mirrored to the GPU lazily
+``_check_drop``        remap_numpy.py:142-147   nothing
+``_remap_data_array``  remap_numpy.py:150-220   ``np.isnan`` pass -> device scan;
+                                                NaN-filled result written by the
+                                                kernel (no MaskedArray detour)
+``_remap_numpy_array`` remap_numpy.py:223-297   one fused launch instead of 1-2
+                                                ``csr.dot`` + ~10 NumPy passes
+=====================  =======================  ================================
+
+xarray is imported lazily (it is an optional dependency of this package; the hot
+path below it, :func:`remap_array`, works on plain arrays and CUDA tensors).
+"""
+
+from __future__ import annotations
+
+import sys
+
+import numpy as np
+
+from . import engine
+from .mapfile import WeightMatrix, coo_to_csr, open_map
+
+
+def _xr():
+    import xarray as xr
+    return xr
+
+
+def _remap_numpy(remapper, ds, renormalization_threshold):
+    """Remap a Dataset or DataArray (reference remap_numpy.py:19-69)."""
+    xr = _xr()
+    map_filename = remapper.map_filename
+    if map_filename is None:
+        raise ValueError('No mapping file has been defined')
+
+    _load_mapping(remapper)
+
+    src_grid_dims = remapper._ds_map['src_grid_dims'].values[::-1]
+
+    for index, dim in enumerate(remapper.src_descriptor.dims):
+        if src_grid_dims[index] != ds.sizes[dim]:
+            raise ValueError(
+                f"data set and remapping source dimension {dim} don't "
+                f'have the same size: {src_grid_dims[index]} != '
+                f'{ds.sizes[dim]}'
+            )
+
+    if isinstance(ds, xr.DataArray):
+        ds_remap = _remap_data_array(ds, remapper, renormalization_threshold)
+    elif isinstance(ds, xr.Dataset):
+        drop = [var for var in ds.data_vars if _check_drop(remapper, ds[var])]
+        ds_remap = ds.drop_vars(drop)
+        ds_remap = ds_remap.map(
+            _remap_data_array,
+            keep_attrs=True,
+            args=(remapper, renormalization_threshold),
+        )
+    else:
+        raise TypeError('ds not an xarray Dataset or DataArray.')
+
+    # history / mesh_name attributes exactly as the reference writes them (:59-67)
+    current_hist = ' '.join(sys.argv[:])
+    if 'history' in ds_remap.attrs:
+        newhist = '\n'.join([ds_remap.attrs['history'], current_hist])
+    else:
+        newhist = current_hist
+    ds_remap.attrs['history'] = newhist
+    ds_remap.attrs['mesh_name'] = remapper.dst_descriptor.mesh_name
+    return ds_remap
+
+
+def _load_mapping(remapper):
+    """Load weights once and cache them on the remapper (remap_numpy.py:72-139)."""
+    if remapper._ds_map is not None:
+        return
+
+    src_descriptor = remapper.src_descriptor
+    dst_descriptor = remapper.dst_descriptor
+
+    ds_map = open_map(remapper.map_filename)
+    n_a = ds_map.sizes['n_a']
+    n_b = ds_map.sizes['n_b']
+
+    n_source_dims = len(src_descriptor.dims)
+    src_grid_rank = ds_map.sizes['src_grid_rank']
+    n_destination_dims = len(dst_descriptor.dims)
+    dst_grid_rank = ds_map.sizes['dst_grid_rank']
+
+    if n_source_dims != src_grid_rank or n_destination_dims != dst_grid_rank:
+        raise ValueError(
+            f'The number of source and/or destination dimensions does not '
+            f'match the expected \n'
+            f'number of source and destination dimensions in the mapping '
+            f'file. \n'
+            f'{n_source_dims} != {src_grid_rank} and/or {n_destination_dims} '
+            f'!= {dst_grid_rank}'
+        )
+
+    # Fortran order in the file -> reverse (remap_numpy.py:108-110)
+    src_grid_dims = ds_map['src_grid_dims'].values[::-1]
+    dst_grid_dims = ds_map['dst_grid_dims'].values[::-1]
+
+    for index, dim in enumerate(src_descriptor.dims):
+        dim_size = src_descriptor.dim_sizes[index]
+        check_dim_size = src_grid_dims[index]
+        if dim_size != check_dim_size:
+            raise ValueError(
+                f'source mesh descriptor and remapping source dimension '
+                f"{dim} don't have the same size: \n"
+                f'{dim_size} != {check_dim_size}'
+            )
+    for index, dim in enumerate(dst_descriptor.dims):
+        dim_size = dst_descriptor.dim_sizes[index]
+        check_dim_size = dst_grid_dims[index]
+        if dim_size != check_dim_size:
+            raise ValueError(
+                f'dest. mesh descriptor and remapping dest. dimension '
+                f"{dim} don't have the same size: \n"
+                f'{dim_size} != {check_dim_size}'
+            )
+
+    col = np.asarray(ds_map['col'].values).astype(np.int64) - 1
+    row = np.asarray(ds_map['row'].values).astype(np.int64) - 1
+    s = ds_map['S'].values
+    indptr, indices, data = coo_to_csr(s, row, col, n_b, n_a)
+    frac_b = np.asarray(ds_map['frac_b'].values, dtype=np.float64)
+    remapper._matrix = WeightMatrix(indptr, indices, data, (n_b, n_a), frac_b)
+    remapper._ds_map = ds_map
+
+
+def _check_drop(remapper, da):
+    """Variables with some but not all source dims are dropped (:142-147)."""
+    src_dims = remapper.src_descriptor.dims
+    present = [dim in da.dims for dim in src_dims]
+    return bool(np.any(present) and not np.all(present))
+
+
+def _remap_data_array(da, remapper, renormalization_threshold):
+    """Remap one DataArray (reference remap_numpy.py:150-220)."""
+    xr = _xr()
+    src_dims = remapper.src_descriptor.dims
+    dst_dims = remapper.dst_descriptor.dims
+
+    present = [dim in da.dims for dim in src_dims]
+    if not np.any(present):
+        return da                       # nothing to remap (:159-161)
+    if not np.all(present):
+        raise ValueError(
+            'Data array with some (but not all) required source dims cannot '
+            'be remapped and should have been dropped.'
+        )
+
+    dims = []
+    remap_axes = []
+    dst_dims_added = False
+    for index, dim in enumerate(da.dims):
+        if dim in src_dims:
+            remap_axes.append(index)
+            if not dst_dims_added:
+                dims.extend(dst_dims)
+                dst_dims_added = True
+        else:
+            dims.append(dim)
+
+    coord_dict = {}
+    for coord in da.coords:
+        touches_src = np.any([dim in da.coords[coord].dims for dim in src_dims])
+        if not touches_src:
+            coord_dict[coord] = {
+                'dims': da.coords[coord].dims,
+                'data': da.coords[coord].values,
+            }
+    coord_dict.update(remapper.dst_descriptor.coords)
+
+    # The reference wraps the field in a MaskedArray iff it holds any NaN
+    # (:201-204) and xarray turns the returned MaskedArray back into NaNs
+    # (:209-218); remap_array does both on the device (any-NaN scan, NaN fill).
+    remapped_field = remap_array(remapper, da.values, remap_axes,
+                                 renormalization_threshold)
+
+    array_dict = {
+        'coords': coord_dict,
+        'attrs': da.attrs,
+        'dims': dims,
+        'data': remapped_field,
+        'name': da.name,
+    }
+    return xr.DataArray.from_dict(array_dict)
+
+
+def _dst_dims(remapper):
+    return [int(d) for d in
+            np.asarray(remapper._ds_map['dst_grid_dims'].values)[::-1]]
+
+
+def _remap_numpy_array(remapper, in_field, remap_axes,
+                       renormalization_threshold):
+    """Drop-in for the reference's array-level routine (remap_numpy.py:223-297):
+    same arguments, returns a float64 ``numpy.ma.MaskedArray`` whose mask is the
+    reference's (``~(S@mask > thr)`` or ``~(frac_b > 0)``)."""
+    is_ma = isinstance(in_field, np.ma.MaskedArray)
+    masked = is_ma and renormalization_threshold is not None
+    valid = np.logical_not(np.ma.getmaskarray(in_field)) if masked else None
+    data = np.ma.getdata(in_field) if is_ma else in_field
+    out, keep = engine.apply_weights(
+        remapper._matrix, _dst_dims(remapper), data, list(remap_axes),
+        renormalization_threshold if masked else None,
+        valid=valid, mode='masked' if masked else 'fracb',
+        device=getattr(remapper, 'device', None), want_keep=True)
+    return np.ma.masked_array(out, mask=np.logical_not(keep))
+
+
+def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
+                return_torch=False):
+    """NaN-filled remap of a plain array or CUDA tensor (new, not in the
+    reference): what ``_remap_data_array`` computes for ``da.values``, i.e.
+    ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch."""
+    if remapper.map_filename is None and remapper._matrix is None:
+        raise ValueError('No mapping file has been defined')
+    _load_mapping(remapper)
+    return engine.apply_weights(
+        remapper._matrix, _dst_dims(remapper), field, list(remap_axes),
+        renormalization_threshold, mode='auto',
+        device=getattr(remapper, 'device', None), return_torch=return_torch)
