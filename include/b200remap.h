@@ -66,8 +66,9 @@ extern "C" {
 
 /* kernel selection (0 = let the library choose from K and the row-length profile) */
 #define B200REMAP_KERNEL_AUTO     0
-#define B200REMAP_KERNEL_LANES_K  1  /* lanes across K, one thread per (row, K-chunk)   */
-#define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums */
+#define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
+#define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
+#define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count (default)  */
 
 typedef struct b200remap_csr b200remap_csr;
 
@@ -115,9 +116,16 @@ B200REMAP_API int b200remap_any_nan(const void *X, int x_dtype, int64_t n, int32
 B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
                         int64_t rows, int64_t cols, void *cuda_stream);
 
+/* diagnostic: q[i] = a[i] / b[i] (device pointers) through the library's shared-reciprocal
+ * division, which must equal IEEE-754 division bit for bit (pinned by the test-suite) */
+B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, double *q, int64_t n,
+                           void *cuda_stream);
+
 /* tuning knobs for experiments (process-wide; 0 restores the default):
- *   0: threads per CTA of the LANES_K kernel   1: load cache policy (0 default,1 L1 no-allocate,2 L1 evict-last)
- *   2: nonzeros in flight per lane (2,4,8)     3: force vector width (1,2,4)            */
+ *   0: target threads per CTA (32..384, default 320)   1: gather cache policy (0 default, 1 L1 no-allocate)
+ *   3: cap on the vector width (1, 2, 4)               4: binning segment length in units of 32 rows
+ *                                                         (read by b200remap_csr_create; default 128)
+ *   5: largest entry count with straight-line code in the BINNED kernel (4, 6 (default) or 8) */
 B200REMAP_API int b200remap_set_tunable(int which, int value);
 
 #ifdef __cplusplus

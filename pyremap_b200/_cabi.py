@@ -15,7 +15,7 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK = 0, 1, 2
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED = 0, 1, 2, 3
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_abi_version', 'b200remap_last_error', 'b200remap_device_count',
     'b200remap_device_arch', 'b200remap_csr_create', 'b200remap_csr_destroy',
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
-    'b200remap_transpose', 'b200remap_set_tunable',
+    'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
 )
 
 
@@ -84,10 +84,12 @@ def load_library():
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
+        lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
         for name in ('b200remap_device_count', 'b200remap_device_arch',
                      'b200remap_csr_create', 'b200remap_csr_info',
                      'b200remap_spmm', 'b200remap_any_nan',
-                     'b200remap_transpose', 'b200remap_set_tunable'):
+                     'b200remap_transpose', 'b200remap_set_tunable',
+                     'b200remap_debug_divide'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -178,4 +180,10 @@ def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0):
     check(load_library().b200remap_transpose(
         ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), int(elem_size),
         int(nbatch), int(rows), int(cols),
+        ctypes.c_void_p(stream) if stream else None))
+
+
+def debug_divide(a_ptr, b_ptr, q_ptr, n, stream=0):
+    check(load_library().b200remap_debug_divide(
+        ctypes.c_void_p(a_ptr), ctypes.c_void_p(b_ptr), ctypes.c_void_p(q_ptr), int(n),
         ctypes.c_void_p(stream) if stream else None))

@@ -85,24 +85,25 @@ def sweep_c3(args):
         tag = 'C3 masked' if masked else 'C3 unmasked'
         for nb in (1, 8):
             nbytes = alg_bytes(csr, K) * nb
-            variants = [(256, 0, 4, 4)]
+            # (kernel, target threads, gather policy, max straight-line class)
+            variants = [(3, 320, 0, 6)]
             if args.full:
-                variants += [(128, 0, 4, 4), (64, 0, 4, 4), (256, 1, 4, 4), (256, 2, 4, 4),
-                             (256, 0, 2, 4), (256, 0, 8, 4), (128, 1, 4, 4), (128, 0, 8, 4),
-                             (256, 1, 8, 4), (256, 0, 4, 2), (128, 1, 2, 4), (256, 1, 2, 4)]
-            for threads, pol, unroll, vec in variants:
-                for which, v in ((0, threads), (1, pol), (2, unroll), (3, vec)):
+                variants += [(3, 160, 0, 6), (3, 320, 0, 8), (3, 160, 0, 8), (3, 320, 0, 4),
+                             (3, 160, 0, 4), (3, 80, 0, 6), (3, 320, 1, 6), (1, 320, 0, 0),
+                             (1, 160, 0, 0)]
+            for kern, threads, pol, maxn in variants:
+                for which, v in ((0, threads), (1, pol), (5, maxn)):
                     _cabi.set_tunable(which, v)
-                ms, best = time_launch(lambda i: run_spmm(csr, ring, y, K, nb, mode, i, 1))
-                report(f'{tag} x{nb}', f'thr={threads} pol={pol} unroll={unroll} vec={vec}',
+                ms, best = time_launch(lambda i: run_spmm(csr, ring, y, K, nb, mode, i, kern))
+                report(f'{tag} x{nb}', f'kernel={kern} thr={threads} pol={pol} maxn={maxn}',
                        ms, best, nbytes)
-            for which in range(4):
+            for which in range(6):
                 _cabi.set_tunable(which, 0)
         if masked:
             # fp32 input
             ring32 = make_ring(m.n_a, K, 4, True, torch.float32)
             nbytes = alg_bytes(csr, K, 4) * 4
-            ms, best = time_launch(lambda i: run_spmm(csr, ring32, y, K, 4, mode, i, 1))
+            ms, best = time_launch(lambda i: run_spmm(csr, ring32, y, K, 4, mode, i, 0))
             report('C3 masked f32-in x4', 'default', ms, best, nbytes)
             del ring32
         del ring
@@ -127,15 +128,16 @@ def sweep_c2(args):
     ring = make_ring(m.n_a, 60, 12, True)
     y = torch.empty((12, m.n_b, 60), dtype=torch.float64, device='cuda')
     nbytes = alg_bytes(csr, 720)
-    ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, 1))
-    report('C2 masked (12,nCells,60)', 'batched x12 K=60', ms, best, nbytes)
+    for kern in (3, 1):
+        ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, kern))
+        report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern}', ms, best, nbytes)
     flat = ring.permute(1, 0, 2).reshape(1, m.n_a, 720).contiguous()
     y2 = torch.empty((1, m.n_b, 720), dtype=torch.float64, device='cuda')
-    for pol in (0, 1):
-        _cabi.set_tunable(1, pol)
-        ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, 1))
-        report('C2 masked [nCells,720]', f'flat K=720 pol={pol}', ms, best, nbytes)
-    _cabi.set_tunable(1, 0)
+    for kern, maxn in ((3, 6), (3, 8), (1, 0)):
+        _cabi.set_tunable(5, maxn)
+        ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, kern))
+        report('C2 masked [nCells,720]', f'flat K=720 kernel={kern} maxn={maxn}', ms, best, nbytes)
+    _cabi.set_tunable(5, 0)
 
 
 def sweep_c1(args):
@@ -143,8 +145,9 @@ def sweep_c1(args):
     csr = device_csr(m)
     x = torch.randn((1, m.n_a, 10), dtype=torch.float64, device='cuda')
     y = torch.empty((1, m.n_b, 10), dtype=torch.float64, device='cuda')
-    ms, best = time_launch(lambda i: run_spmm(csr, x, y, 10, 1, _cabi.MODE_FRACB, i, 1), reps=50)
-    report('C1 unmasked K=10', 'lanes_k (latency)', ms, best, alg_bytes(csr, 10))
+    for kern in (3, 1):
+        ms, best = time_launch(lambda i: run_spmm(csr, x, y, 10, 1, _cabi.MODE_FRACB, i, kern), reps=50)
+        report('C1 unmasked K=10', f'kernel={kern} (latency)', ms, best, alg_bytes(csr, 10))
 
 
 def sweep_c4(args):
@@ -155,7 +158,7 @@ def sweep_c4(args):
         x = make_ring(m.n_a, K, 2, False)
         x[:, :: 97, :] = float('nan')
         y = torch.empty((1, m.n_b, K), dtype=torch.float64, device='cuda')
-        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k')):
+        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (3, 'binned')):
             ms, best = time_launch(lambda i: run_spmm(csr, x, y, K, 1, _cabi.MODE_MASKED, i, kernel))
             report(f'C4 masked K={K}', name, ms, best, alg_bytes(csr, K))
 
