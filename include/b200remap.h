@@ -68,7 +68,8 @@ extern "C" {
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
-#define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count (default)  */
+#define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count            */
+#define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised TMA bulk-gather pipeline  */
 
 typedef struct b200remap_csr b200remap_csr;
 
@@ -125,7 +126,8 @@ B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, doubl
  *   0: target threads per CTA (32..384, default 320)   1: gather cache policy (0 default, 1 L1 no-allocate)
  *   3: cap on the vector width (1, 2, 4)               4: binning segment length in units of 32 rows
  *                                                         (read by b200remap_csr_create; default 128)
- *   5: largest entry count with straight-line code in the BINNED kernel (4, 6 (default) or 8) */
+ *   5: largest entry count with straight-line code in the BINNED kernel (4, 6 (default) or 8)
+ *   2: cap on the pipeline stages of the TMA kernel (2..6)   6: its shared-memory budget in KB (default 200) */
 B200REMAP_API int b200remap_set_tunable(int which, int value);
 
 #ifdef __cplusplus
