@@ -325,7 +325,7 @@ def run_b200(args):
     achieved = b_slice * BATCH / (launch_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel': 'tma_kernel<double,MODE=%d>' % mode_code,
+                'kernel': 'staged_kernel<double,MODE=%d,LDGSTS>' % mode_code,
                 'launch_ms': launch_ms, 'algorithmic_bytes_per_launch': b_slice * BATCH,
                 'algorithmic_bytes_per_slice': b_slice,
                 'full_x_bytes_per_slice': b_slice_full,

@@ -69,7 +69,8 @@ extern "C" {
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
 #define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count            */
-#define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised TMA bulk-gather pipeline  */
+#define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised pipeline, TMA bulk gathers */
+#define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers (default)      */
 
 typedef struct b200remap_csr b200remap_csr;
 

@@ -15,7 +15,8 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA = 0, 1, 2, 3, 4
+(KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA,
+ KERNEL_STAGED) = 0, 1, 2, 3, 4, 5
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
