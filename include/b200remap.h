@@ -70,7 +70,8 @@ extern "C" {
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
 #define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count            */
 #define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised pipeline, TMA bulk gathers */
-#define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers (default)      */
+#define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers                */
+#define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
 
 typedef struct b200remap_csr b200remap_csr;
 
@@ -128,7 +129,8 @@ B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, doubl
  *   3: cap on the vector width (1, 2, 4)               4: binning segment length in units of 32 rows
  *                                                         (read by b200remap_csr_create; default 128)
  *   5: largest entry count with straight-line code in the BINNED kernel (4, 6 (default) or 8)
- *   2: cap on the pipeline stages of the TMA kernel (2..6)   6: its shared-memory budget in KB (default 200) */
+ *   2: cap on the pipeline stages of the staged kernels (2..6)   6: their shared-memory budget in KB (default 200)
+ *   7: persistent CTAs per SM of the PBIN kernel (default: occupancy limit) */
 B200REMAP_API int b200remap_set_tunable(int which, int value);
 
 #ifdef __cplusplus
