@@ -114,6 +114,12 @@ B200REMAP_API int b200remap_spmm(const b200remap_csr *csr, const void *X, int x_
 B200REMAP_API int b200remap_any_nan(const void *X, int x_dtype, int64_t n, int32_t *flag_dev,
                       void *cuda_stream);
 
+/* The same test on a HOST buffer with `threads` CPU threads and early exit (*out = 0/1): used
+ * when the field lives in host memory and only the source rows the map touches are copied
+ * to the GPU -- the branch test of remap_numpy.py:202-204 is over the whole variable. */
+B200REMAP_API int b200remap_host_any_nan(const void *X, int x_dtype, int64_t n, int threads,
+                           int *out);
+
 /* out[b][c][r] = in[b][r][c]  (batched 2-D transpose; rows x cols -> cols x rows),
  * used for field-major layouts either side of the product.  elem_size is 4 or 8. */
 B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
@@ -125,10 +131,9 @@ B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, doubl
                            void *cuda_stream);
 
 /* tuning knobs for experiments (process-wide; 0 restores the default):
- *   0: target threads per CTA (32..384, default 320)   1: gather cache policy (0 default, 1 L1 no-allocate)
+ *   0: target threads per CTA (32..384, default 160)
  *   3: cap on the vector width (1, 2, 4)               4: binning segment length in units of 32 rows
  *                                                         (read by b200remap_csr_create; default 128)
- *   5: largest entry count with straight-line code in the BINNED kernel (4, 6 (default) or 8)
  *   2: cap on the pipeline stages of the staged kernels (2..6)   6: their shared-memory budget in KB (default 200)
  *   7: persistent CTAs per SM of the PBIN kernel (default: occupancy limit) */
 B200REMAP_API int b200remap_set_tunable(int which, int value);

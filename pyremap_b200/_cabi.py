@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_device_arch', 'b200remap_csr_create', 'b200remap_csr_destroy',
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
+    'b200remap_host_any_nan',
 )
 
 
@@ -86,11 +87,12 @@ def load_library():
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
         lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
+        lib.b200remap_host_any_nan.argtypes = [vp, i32, i64, i32, ctypes.POINTER(i32)]
         for name in ('b200remap_device_count', 'b200remap_device_arch',
                      'b200remap_csr_create', 'b200remap_csr_info',
                      'b200remap_spmm', 'b200remap_any_nan',
                      'b200remap_transpose', 'b200remap_set_tunable',
-                     'b200remap_debug_divide'):
+                     'b200remap_debug_divide', 'b200remap_host_any_nan'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -188,3 +190,19 @@ def debug_divide(a_ptr, b_ptr, q_ptr, n, stream=0):
     check(load_library().b200remap_debug_divide(
         ctypes.c_void_p(a_ptr), ctypes.c_void_p(b_ptr), ctypes.c_void_p(q_ptr), int(n),
         ctypes.c_void_p(stream) if stream else None))
+
+
+def host_any_nan(array, threads=None):
+    """True iff the C-contiguous float32/float64 numpy array holds a NaN (native, early exit)."""
+    import numpy as np
+    a = array
+    if a.dtype not in (np.float64, np.float32) or not a.flags.c_contiguous:
+        raise ValueError('host_any_nan needs a C-contiguous float32/float64 array')
+    if threads is None:
+        threads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
+                      else (os.cpu_count() or 1))
+    out = ctypes.c_int(0)
+    check(load_library().b200remap_host_any_nan(
+        ctypes.c_void_p(a.ctypes.data), F64 if a.dtype == np.float64 else F32, a.size,
+        int(threads), ctypes.byref(out)))
+    return bool(out.value)
