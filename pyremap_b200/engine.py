@@ -168,6 +168,11 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
     if lay.n_dst != matrix.shape[0]:
         raise ValueError(f'destination dims {lay.dst_dims} do not match the map '
                          f'({matrix.shape[0]} rows)')
+    if (valid is None and not want_keep and not return_torch and lay.adjacent
+            and not (lay.L == 1 and lay.B > 1) and lay.L > 0 and lay.n_dst > 0):
+        host = _host_view(field, torch)
+        if host is not None:
+            return _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch)
     csr = matrix.on_device(device.index)
 
     with torch.cuda.device(device):
@@ -249,3 +254,106 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
             out = out.cpu().numpy()
             keep = None if keep is None else keep.cpu().numpy()
     return (out, keep) if want_keep else out
+
+
+# --------------------------------------------------------------------------
+# host arrays: streamed H2D -> kernel -> D2H
+# --------------------------------------------------------------------------
+_STREAMS = {}
+
+
+def _side_streams(device, torch):
+    key = (device.index,)
+    if key not in _STREAMS:
+        _STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return _STREAMS[key]
+
+
+def _host_view(field, torch):
+    """A C-contiguous float32/float64 CPU tensor sharing ``field``'s memory, or None."""
+    if isinstance(field, torch.Tensor):
+        if field.is_cuda or field.dtype not in (torch.float64, torch.float32):
+            return None
+        return field if field.is_contiguous() else None
+    a = field
+    if isinstance(a, np.ma.MaskedArray) or not isinstance(a, np.ndarray):
+        return None
+    if a.dtype not in (np.float64, np.float32) or not a.dtype.isnative:
+        return None
+    if not a.flags.c_contiguous or not a.flags.writeable or a.size == 0:
+        return None
+    return torch.from_numpy(a)
+
+
+def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch):
+    """Host field in, host result out, one fused launch per leading-axis slice.
+
+    * branch selection over the whole variable on the host (native early-exit scan),
+      because only the source rows the map touches are copied to the GPU
+      (regional maps: a few contiguous runs, :meth:`WeightMatrix.cover`);
+    * per slice: H2D on a copy stream, kernel on the current stream, D2H into pinned
+      memory on a second copy stream -- the three overlap across slices (PCIe is full
+      duplex) with double-buffered device tensors.
+    """
+    if mode == 'auto':
+        if threshold is None:
+            mode_code = MODE_FRACB
+        else:
+            mode_code = MODE_MASKED if _cabi.host_any_nan(host.numpy()) else MODE_FRACB
+    else:
+        mode_code = {'raw': MODE_RAW, 'fracb': MODE_FRACB, 'masked': MODE_MASKED}[mode]
+    if mode_code == MODE_MASKED and threshold is None:
+        raise ValueError('the masked branch needs a renormalization threshold')
+    thr = float(threshold) if threshold is not None else 0.0
+
+    cov = matrix.cover()
+    if cov is None:
+        csr = matrix.on_device(device.index)
+        runs, n_x = [(0, lay.n_src, 0)], lay.n_src
+    else:
+        csr = matrix.on_device_cover(device.index)
+        runs, n_x = cov['runs'], cov['n_cover']
+    if mode_code == MODE_FRACB and not csr.has_frac_b:
+        raise ValueError('the map has no frac_b; cannot take the unmasked branch')
+
+    B, L = lay.B, lay.L
+    src = host.view(B, lay.n_src, L)
+    code = _dtype_code(src, torch)
+    with torch.cuda.device(device):
+        compute = torch.cuda.current_stream(device)
+        s_in, s_out = _side_streams(device, torch)
+        out = torch.empty((B, lay.n_dst, L), dtype=torch.float64, pin_memory=True)
+        nbuf = min(2, B)
+        xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
+        yd = [torch.empty((lay.n_dst, L), dtype=torch.float64, device=device) for _ in range(nbuf)]
+        x_free = [None] * nbuf      # kernel that last read xd[i] has finished
+        y_free = [None] * nbuf      # D2H that last read yd[i] has finished
+        s_in.wait_stream(compute)
+        for b in range(B):
+            i = b % nbuf
+            if x_free[i] is not None:
+                s_in.wait_event(x_free[i])
+            with torch.cuda.stream(s_in):
+                for start, length, pos in runs:
+                    xd[i][pos:pos + length].copy_(src[b, start:start + length], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            compute.wait_event(ready)
+            if y_free[i] is not None:
+                compute.wait_event(y_free[i])
+            csr.spmm(xd[i].data_ptr(), code, L, L, 1, 0, yd[i].data_ptr(), L, 0, mode_code, thr,
+                     kernel=kernel, stream=compute.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(compute)
+            x_free[i] = done
+            s_out.wait_event(done)
+            with torch.cuda.stream(s_out):
+                out[b].copy_(yd[i], non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(s_out)
+            y_free[i] = fin
+        for t in xd + yd:            # the side streams still use these buffers
+            t.record_stream(s_in)
+            t.record_stream(s_out)
+        s_out.synchronize()
+    return out.numpy().reshape(lay.out_shape)

@@ -225,3 +225,34 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), f
                 assert 'scipy.sparse' not in text or f == 'mapfile.py', f
+
+
+def test_host_any_nan_native_cpu():
+    rng = np.random.default_rng(0)
+    for dtype in (np.float64, np.float32):
+        a = rng.normal(size=300_001).astype(dtype)
+        assert _cabi.host_any_nan(a) is False
+        for pos in (0, 150_000, 300_000):
+            b = a.copy()
+            b[pos] = np.nan
+            assert _cabi.host_any_nan(b) is True and _cabi.host_any_nan(b, threads=1) is True
+    assert _cabi.host_any_nan(np.zeros(0)) is False
+    with pytest.raises(ValueError):
+        _cabi.host_any_nan(np.zeros(4, dtype=np.int32))
+
+
+def test_cover_renumbering_is_monotonic_and_complete():
+    m = syn.make_c3(scale=0.02)
+    ip, ix, d = mapfile.coo_to_csr(m.S, m.row.astype(np.int64) - 1, m.col.astype(np.int64) - 1,
+                                   m.n_b, m.n_a)
+    W = mapfile.WeightMatrix(ip, ix, d, (m.n_b, m.n_a), m.frac_b)
+    cov = W.cover()
+    assert cov is not None and len(cov['runs']) <= 64
+    lut = np.full(m.n_a, -1)
+    for start, length, pos in cov['runs']:
+        lut[start:start + length] = np.arange(pos, pos + length)
+    assert np.array_equal(lut[ix], cov['indices']) and cov['indices'].min() >= 0
+    assert cov['n_cover'] == sum(r[1] for r in cov['runs']) < 0.7 * m.n_a
+    full = syn.make_c1(30.0, 15.0)
+    ip, ix, d = mapfile.coo_to_csr(full.S, full.row - 1, full.col - 1, full.n_b, full.n_a)
+    assert mapfile.WeightMatrix(ip, ix, d, (full.n_b, full.n_a), full.frac_b).cover() is None
