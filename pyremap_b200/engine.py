@@ -262,6 +262,30 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
 _STREAMS = {}
 
 
+class _Trace:
+    """Phase timer of the streamed path, printed when ``B200REMAP_TRACE=1``."""
+
+    def __init__(self):
+        import os
+        import time
+        self.on = os.environ.get('B200REMAP_TRACE') == '1'
+        self.clock = time.perf_counter
+        self.t = self.clock()
+        self.marks = []
+
+    def mark(self, name):
+        if self.on:
+            now = self.clock()
+            self.marks.append((name, (now - self.t) * 1e3))
+            self.t = now
+
+    def report(self, what):
+        if self.on:
+            import sys
+            print('[b200remap] ' + what + ': ' +
+                  ', '.join(f'{n} {ms:.2f} ms' for n, ms in self.marks), file=sys.stderr)
+
+
 def _side_streams(device, torch):
     key = (device.index,)
     if key not in _STREAMS:
@@ -295,6 +319,7 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
       memory on a second copy stream -- the three overlap across slices (PCIe is full
       duplex) with double-buffered device tensors.
     """
+    trace = _Trace()
     if mode == 'auto':
         if threshold is None:
             mode_code = MODE_FRACB
@@ -305,6 +330,7 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     if mode_code == MODE_MASKED and threshold is None:
         raise ValueError('the masked branch needs a renormalization threshold')
     thr = float(threshold) if threshold is not None else 0.0
+    trace.mark('host NaN scan')
 
     cov = matrix.cover()
     if cov is None:
@@ -322,10 +348,12 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     with torch.cuda.device(device):
         compute = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device, torch)
+        trace.mark('weights on device')
         out = torch.empty((B, lay.n_dst, L), dtype=torch.float64, pin_memory=True)
         nbuf = min(2, B)
         xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
         yd = [torch.empty((lay.n_dst, L), dtype=torch.float64, device=device) for _ in range(nbuf)]
+        trace.mark('buffers')
         x_free = [None] * nbuf      # kernel that last read xd[i] has finished
         y_free = [None] * nbuf      # D2H that last read yd[i] has finished
         s_in.wait_stream(compute)
@@ -355,5 +383,8 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
         for t in xd + yd:            # the side streams still use these buffers
             t.record_stream(s_in)
             t.record_stream(s_out)
+        trace.mark('enqueue')
         s_out.synchronize()
+        trace.mark('drain')
+    trace.report(f'streamed remap B={B} L={L} rows_copied={n_x}')
     return out.numpy().reshape(lay.out_shape)
