@@ -125,6 +125,15 @@ B200REMAP_API int b200remap_host_any_nan(const void *X, int x_dtype, int64_t n, 
 B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
                         int64_t rows, int64_t cols, void *cuda_stream);
 
+/* dst[i, :] = src[rows_dev[i], :] for i < n_rows, rows of row_bytes (multiple of 16) bytes;
+ * src rows are src_row_bytes apart.  `src` is any device-accessible pointer -- in particular
+ * pinned (mapped) host memory, which makes this the host->device transfer of exactly the
+ * source rows the map touches (replaces the full-field copy of `da.values`,
+ * remap_numpy.py:201, for regional maps). */
+B200REMAP_API int b200remap_gather_rows(const void *src, void *dst, const int32_t *rows_dev,
+                          int64_t n_rows, int64_t row_bytes, int64_t src_row_bytes,
+                          void *cuda_stream);
+
 /* diagnostic: q[i] = a[i] / b[i] (device pointers) through the library's shared-reciprocal
  * division, which must equal IEEE-754 division bit for bit (pinned by the test-suite) */
 B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, double *q, int64_t n,

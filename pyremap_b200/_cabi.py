@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_device_arch', 'b200remap_csr_create', 'b200remap_csr_destroy',
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
-    'b200remap_host_any_nan',
+    'b200remap_host_any_nan', 'b200remap_gather_rows',
 )
 
 
@@ -88,11 +88,13 @@ def load_library():
         lib.b200remap_set_tunable.argtypes = [i32, i32]
         lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
         lib.b200remap_host_any_nan.argtypes = [vp, i32, i64, i32, ctypes.POINTER(i32)]
+        lib.b200remap_gather_rows.argtypes = [vp, vp, vp, i64, i64, i64, vp]
         for name in ('b200remap_device_count', 'b200remap_device_arch',
                      'b200remap_csr_create', 'b200remap_csr_info',
                      'b200remap_spmm', 'b200remap_any_nan',
                      'b200remap_transpose', 'b200remap_set_tunable',
-                     'b200remap_debug_divide', 'b200remap_host_any_nan'):
+                     'b200remap_debug_divide', 'b200remap_host_any_nan',
+                     'b200remap_gather_rows'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -206,3 +208,10 @@ def host_any_nan(array, threads=None):
         ctypes.c_void_p(a.ctypes.data), F64 if a.dtype == np.float64 else F32, a.size,
         int(threads), ctypes.byref(out)))
     return bool(out.value)
+
+
+def gather_rows(src_ptr, dst_ptr, rows_ptr, n_rows, row_bytes, src_row_bytes, stream=0):
+    check(load_library().b200remap_gather_rows(
+        ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr), ctypes.c_void_p(rows_ptr),
+        int(n_rows), int(row_bytes), int(src_row_bytes),
+        ctypes.c_void_p(stream) if stream else None))

@@ -332,10 +332,22 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     thr = float(threshold) if threshold is not None else 0.0
     trace.mark('host NaN scan')
 
-    cov = matrix.cover()
+    # which source rows travel: everything, a few contiguous runs (pageable memory), or -- when
+    # the field sits in pinned memory the GPU can read directly -- exactly the touched rows
+    rows_dev = None
+    row_bytes = lay.L * host.element_size()
+    zero_copy = host.is_pinned() and row_bytes % 16 == 0 and host.data_ptr() % 16 == 0
+    cov = matrix.cover_exact() if zero_copy else matrix.cover()
     if cov is None:
         csr = matrix.on_device(device.index)
         runs, n_x = [(0, lay.n_src, 0)], lay.n_src
+    elif zero_copy:
+        csr = matrix.on_device_cover(device.index, exact=True)
+        runs, n_x = None, cov['n_cover']
+        key = ('rows_dev', device.index)
+        if key not in cov:
+            cov[key] = torch.from_numpy(cov['rows']).to(device)
+        rows_dev = cov[key]
     else:
         csr = matrix.on_device_cover(device.index)
         runs, n_x = cov['runs'], cov['n_cover']
@@ -362,8 +374,13 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             if x_free[i] is not None:
                 s_in.wait_event(x_free[i])
             with torch.cuda.stream(s_in):
-                for start, length, pos in runs:
-                    xd[i][pos:pos + length].copy_(src[b, start:start + length], non_blocking=True)
+                if rows_dev is not None:
+                    _cabi.gather_rows(src[b].data_ptr(), xd[i].data_ptr(), rows_dev.data_ptr(), n_x,
+                                      row_bytes, row_bytes, s_in.cuda_stream)
+                else:
+                    for start, length, pos in runs:
+                        xd[i][pos:pos + length].copy_(src[b, start:start + length],
+                                                      non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(s_in)
             compute.wait_event(ready)

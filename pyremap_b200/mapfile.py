@@ -222,11 +222,24 @@ class WeightMatrix:
                                'n_cover': n_cover, 'indices': new_idx}
         return self._cover
 
-    def on_device_cover(self, device=0):
+    def cover_exact(self, worthwhile=0.7):
+        """Exactly the touched source rows (sorted), for transfers that can gather row by
+        row (pinned host memory read by the GPU): ``{'rows', 'n_cover', 'indices'}`` or None."""
+        if getattr(self, '_cover_exact', False) is not False:
+            return self._cover_exact
+        self._cover_exact = None
+        touched = np.unique(self.indices)
+        if touched.size and touched.size <= worthwhile * self.shape[1]:
+            self._cover_exact = {
+                'rows': touched.astype(np.int32), 'n_cover': int(touched.size),
+                'indices': np.searchsorted(touched, self.indices).astype(np.int32)}
+        return self._cover_exact
+
+    def on_device_cover(self, device=0, exact=False):
         """``DeviceCSR`` over the covered source rows only (see :meth:`cover`)."""
         from ._cabi import DeviceCSR
-        cov = self.cover()
-        key = ('cover', int(device))
+        cov = self.cover_exact() if exact else self.cover()
+        key = ('cover-exact' if exact else 'cover', int(device))
         if key not in self._device:
             self._device[key] = DeviceCSR(self.indptr, cov['indices'], self.data, self.frac_b,
                                           cov['n_cover'], int(device))
