@@ -323,9 +323,17 @@ def run_b200(args):
     except Exception:
         peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
     achieved = b_slice * BATCH / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:       # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed capture
+        cap = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        if args.mode == 'masked' and args.scale == 1.0:
+            traffic, traffic_src = cap['traffic_bytes_per_launch'], cap['source']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'kernel': 'staged_kernel<double,MODE=%d,LDGSTS>' % mode_code,
+                'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': peak_src,
+                'kernel': 'pbin_kernel<double,VEC=4,MODE=%d>' % mode_code,
                 'launch_ms': launch_ms, 'algorithmic_bytes_per_launch': b_slice * BATCH,
                 'algorithmic_bytes_per_slice': b_slice,
                 'full_x_bytes_per_slice': b_slice_full,
