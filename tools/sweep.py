@@ -86,7 +86,7 @@ def sweep_c3(args):
         for nb in (1, 8):
             nbytes = alg_bytes(csr, K) * nb
             # (kernel, target threads, gather policy, max straight-line class)
-            variants = [(0, 0, 0, 0), (6, 160, 0, 1), (6, 80, 0, 1), (6, 160, 0, 6), (6, 80, 0, 6)]
+            variants = [(0, 0, 0, 0), (6, 160, 0, 5), (6, 160, 0, 6), (6, 160, 0, 7), (6, 160, 0, 8), (6, 80, 0, 7), (6, 80, 0, 8), (6, 160, 0, 1)]
             if args.full:
                 variants += [(7, 40, 0, 0), (7, 320, 0, 0), (3, 160, 0, 6), (5, 0, 0, 0), (1, 160, 0, 0)]
             if args.full > 1:
