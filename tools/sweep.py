@@ -86,9 +86,9 @@ def sweep_c3(args):
         for nb in (1, 8):
             nbytes = alg_bytes(csr, K) * nb
             # (kernel, target threads, gather policy, max straight-line class)
-            variants = [(0, 0, 0, 0), (6, 160, 0, 5), (6, 160, 0, 6), (6, 160, 0, 7), (6, 160, 0, 8), (6, 80, 0, 7), (6, 80, 0, 8), (6, 160, 0, 1)]
+            variants = [(0, 0, 0, 0), (6, 160, 0, 0), (6, 80, 0, 0), (6, 320, 0, 0)]
             if args.full:
-                variants += [(7, 40, 0, 0), (7, 320, 0, 0), (3, 160, 0, 6), (5, 0, 0, 0), (1, 160, 0, 0)]
+                variants += [(3, 160, 0, 6), (5, 0, 0, 0), (4, 0, 0, 0), (1, 160, 0, 0)]
             if args.full > 1:
                 variants += [(3, 160, 0, 6), (3, 320, 0, 8), (3, 160, 0, 8), (3, 320, 0, 4),
                              (3, 160, 0, 4), (3, 80, 0, 6), (3, 320, 1, 6), (1, 320, 0, 0),
@@ -131,12 +131,12 @@ def sweep_c2(args):
     ring = make_ring(m.n_a, 60, 12, True)
     y = torch.empty((12, m.n_b, 60), dtype=torch.float64, device='cuda')
     nbytes = alg_bytes(csr, 720)
-    for kern in (7, 6, 3, 1):
+    for kern in (6, 3, 1):
         ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, kern))
         report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern}', ms, best, nbytes)
     flat = ring.permute(1, 0, 2).reshape(1, m.n_a, 720).contiguous()
     y2 = torch.empty((1, m.n_b, 720), dtype=torch.float64, device='cuda')
-    for kern, maxn in ((0, 0), (7, 0), (6, 6), (3, 6), (1, 0)):
+    for kern, maxn in ((0, 0), (6, 0), (3, 6), (1, 0)):
         _cabi.set_tunable(5, maxn)
         ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, kern))
         report('C2 masked [nCells,720]', f'flat K=720 kernel={kern} maxn={maxn}', ms, best, nbytes)
