@@ -72,6 +72,7 @@ extern "C" {
 #define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised pipeline, TMA bulk gathers */
 #define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers                */
 #define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
+#define B200REMAP_KERNEL_WROW     7  /* warp-autonomous persistent binned tiles, no CTA barrier */
 
 typedef struct b200remap_csr b200remap_csr;
 

@@ -16,7 +16,7 @@ from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
 (KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA,
- KERNEL_STAGED, KERNEL_PBIN) = 0, 1, 2, 3, 4, 5, 6
+ KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW) = 0, 1, 2, 3, 4, 5, 6, 7
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -53,8 +53,8 @@ def load_library():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if _build.is_stale():
+        path = os.environ.get('B200REMAP_LIB') or _build.LIB_PATH   # override: experiment builds
+        if path == _build.LIB_PATH and _build.is_stale():
             try:
                 _build.build_library()
             except Exception as exc:

@@ -86,7 +86,8 @@ def sweep_c3(args):
         for nb in (1, 8):
             nbytes = alg_bytes(csr, K) * nb
             # (kernel, target threads, gather policy, max straight-line class)
-            variants = [(0, 0, 0, 0), (6, 160, 0, 0), (6, 80, 0, 0), (6, 320, 0, 0)]
+            variants = [(0, 0, 0, 0), (6, 160, 0, 0), (7, 0, 0, 0), (7, 0, 0, 12), (7, 0, 0, 6),
+                        (7, 4, 0, 0), (7, 2, 0, 0)]
             if args.full:
                 variants += [(3, 160, 0, 6), (5, 0, 0, 0), (4, 0, 0, 0), (1, 160, 0, 0)]
             if args.full > 1:
@@ -131,12 +132,12 @@ def sweep_c2(args):
     ring = make_ring(m.n_a, 60, 12, True)
     y = torch.empty((12, m.n_b, 60), dtype=torch.float64, device='cuda')
     nbytes = alg_bytes(csr, 720)
-    for kern in (6, 3, 1):
+    for kern in (6, 7, 3, 1):
         ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, kern))
         report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern}', ms, best, nbytes)
     flat = ring.permute(1, 0, 2).reshape(1, m.n_a, 720).contiguous()
     y2 = torch.empty((1, m.n_b, 720), dtype=torch.float64, device='cuda')
-    for kern, maxn in ((0, 0), (6, 0), (3, 6), (1, 0)):
+    for kern, maxn in ((0, 0), (6, 0), (7, 0), (7, 6), (3, 6), (1, 0)):
         _cabi.set_tunable(5, maxn)
         ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, kern))
         report('C2 masked [nCells,720]', f'flat K=720 kernel={kern} maxn={maxn}', ms, best, nbytes)
@@ -148,7 +149,7 @@ def sweep_c1(args):
     csr = device_csr(m)
     x = torch.randn((1, m.n_a, 10), dtype=torch.float64, device='cuda')
     y = torch.empty((1, m.n_b, 10), dtype=torch.float64, device='cuda')
-    for kern in (6, 3, 1):
+    for kern in (6, 7, 3, 1):
         ms, best = time_launch(lambda i: run_spmm(csr, x, y, 10, 1, _cabi.MODE_FRACB, i, kern), reps=50)
         report('C1 unmasked K=10', f'kernel={kern} (latency)', ms, best, alg_bytes(csr, 10))
 
@@ -161,7 +162,7 @@ def sweep_c4(args):
         x = make_ring(m.n_a, K, 2, False)
         x[:, :: 97, :] = float('nan')
         y = torch.empty((1, m.n_b, K), dtype=torch.float64, device='cuda')
-        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (3, 'binned')) + ((6, 'pbin'),) + (((5, 'staged'),) if K % 4 == 0 else ()):
+        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (3, 'binned')) + ((6, 'pbin'), (7, 'wrow')) + (((5, 'staged'),) if K % 4 == 0 else ()):
             ms, best = time_launch(lambda i: run_spmm(csr, x, y, K, 1, _cabi.MODE_MASKED, i, kernel))
             report(f'C4 masked K={K}', name, ms, best, alg_bytes(csr, K))
 
