@@ -73,6 +73,7 @@ extern "C" {
 #define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers                */
 #define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
 #define B200REMAP_KERNEL_WROW     7  /* warp-autonomous persistent binned tiles, no CTA barrier */
+#define B200REMAP_KERNEL_PATCH    8  /* de-duplicated source rows of a row patch staged in smem  */
 
 typedef struct b200remap_csr b200remap_csr;
 

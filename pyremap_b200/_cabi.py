@@ -16,7 +16,7 @@ from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
 (KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA,
- KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW) = 0, 1, 2, 3, 4, 5, 6, 7
+ KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW, KERNEL_PATCH) = 0, 1, 2, 3, 4, 5, 6, 7, 8
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
