@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument('--mode', default='masked', choices=['masked', 'unmasked'])
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-slices', type=int, default=4, help='slices per e2e call')
+    ap.add_argument('--e2e-slices', type=int, default=8, help='slices per e2e call')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
     return ap.parse_args()
 
@@ -333,7 +333,9 @@ def run_b200(args):
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': peak_src,
-                'kernel': 'pbin_kernel<double,VEC=4,MODE=%d>' % mode_code,
+                # AUTO (b200remap_spmm): batched masked sweeps -> wrow_kernel, else pbin_kernel
+                'kernel': ('wrow_kernel' if args.mode == 'masked' and BATCH >= 2 else 'pbin_kernel')
+                + '<double,VEC=4,MODE=%d>' % mode_code,
                 'launch_ms': launch_ms, 'algorithmic_bytes_per_launch': b_slice * BATCH,
                 'algorithmic_bytes_per_slice': b_slice,
                 'full_x_bytes_per_slice': b_slice_full,
@@ -402,14 +404,16 @@ def measure_e2e(args, torch, dist, m, matrix, device, world, ring):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     assert out.shape == (T, m.dst_descriptor.dim_sizes[0], m.dst_descriptor.dim_sizes[1], N_LEVELS)
-    cov = matrix.cover_exact()                  # pinned input: the GPU gathers the touched rows
+    cov = matrix.cover_exact()                  # pinned input: exactly the touched rows travel
     rows_copied = cov['n_cover'] if cov else m.n_a
+    n_runs = int(cov['run_start'].size) if cov else 1
     return {'value': world * calls * T / dt, 'unit': UNIT,
             'h2d_bytes_per_step': int(T * rows_copied * N_LEVELS * 8),
             'd2h_bytes_per_step': int(T * m.n_b * N_LEVELS * 8),
             'step': f'one call of Remapper.remap_array(pinned host ndarray (Time={T}, nCells, '
                     f'nVertLevels)) -> host ndarray; {rows_copied} of {m.n_a} source rows copied per '
-                    f'slice (exactly the rows the map touches, gathered by the GPU from pinned memory)',
+                    f'slice (exactly the rows the map touches: {n_runs} contiguous runs, one batched '
+                    f'DMA submission per slice, full duplex with the D2H of results)',
             'calls_timed': calls, 'slices_per_call': T, 'ms_per_slice': dt / (calls * T) * 1e3,
             'host_nan_scan': 'whole variable, native early-exit scan (branch selection)'}
 

@@ -73,7 +73,6 @@ extern "C" {
 #define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers                */
 #define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
 #define B200REMAP_KERNEL_WROW     7  /* warp-autonomous persistent binned tiles, no CTA barrier */
-#define B200REMAP_KERNEL_PATCH    8  /* de-duplicated source rows of a row patch staged in smem  */
 
 typedef struct b200remap_csr b200remap_csr;
 
@@ -135,6 +134,17 @@ B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, 
 B200REMAP_API int b200remap_gather_rows(const void *src, void *dst, const int32_t *rows_dev,
                           int64_t n_rows, int64_t row_bytes, int64_t src_row_bytes,
                           void *cuda_stream);
+
+/* n_runs independent copies dst + dst_off[i] <- src + src_off[i] of bytes[i] bytes (offsets and
+ * sizes are host arrays, in bytes) enqueued on `cuda_stream` as ONE batched DMA submission
+ * (cudaMemcpyBatchAsync; a loop of cudaMemcpyAsync when use_batch == 0 or the batch API refuses).
+ * With `src` in pinned host memory this moves the contiguous runs of touched source rows
+ * through the copy engines, which -- unlike SM loads from host memory -- run at full PCIe rate
+ * while a device->host copy of results is in flight (replaces the full-field copy of
+ * `da.values`, remap_numpy.py:201).  `cuda_stream` must be a real (non-legacy) stream. */
+B200REMAP_API int b200remap_copy_runs(const void *src, void *dst, const int64_t *src_off,
+                        const int64_t *dst_off, const int64_t *bytes, int64_t n_runs,
+                        int use_batch, void *cuda_stream);
 
 /* diagnostic: q[i] = a[i] / b[i] (device pointers) through the library's shared-reciprocal
  * division, which must equal IEEE-754 division bit for bit (pinned by the test-suite) */

@@ -16,7 +16,7 @@ from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
 (KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA,
- KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW, KERNEL_PATCH) = 0, 1, 2, 3, 4, 5, 6, 7, 8
+ KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW) = 0, 1, 2, 3, 4, 5, 6, 7
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_device_arch', 'b200remap_csr_create', 'b200remap_csr_destroy',
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
-    'b200remap_host_any_nan', 'b200remap_gather_rows',
+    'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
 )
 
 
@@ -89,12 +89,13 @@ def load_library():
         lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
         lib.b200remap_host_any_nan.argtypes = [vp, i32, i64, i32, ctypes.POINTER(i32)]
         lib.b200remap_gather_rows.argtypes = [vp, vp, vp, i64, i64, i64, vp]
+        lib.b200remap_copy_runs.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
         for name in ('b200remap_device_count', 'b200remap_device_arch',
                      'b200remap_csr_create', 'b200remap_csr_info',
                      'b200remap_spmm', 'b200remap_any_nan',
                      'b200remap_transpose', 'b200remap_set_tunable',
                      'b200remap_debug_divide', 'b200remap_host_any_nan',
-                     'b200remap_gather_rows'):
+                     'b200remap_gather_rows', 'b200remap_copy_runs'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -214,4 +215,20 @@ def gather_rows(src_ptr, dst_ptr, rows_ptr, n_rows, row_bytes, src_row_bytes, st
     check(load_library().b200remap_gather_rows(
         ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr), ctypes.c_void_p(rows_ptr),
         int(n_rows), int(row_bytes), int(src_row_bytes),
+        ctypes.c_void_p(stream) if stream else None))
+
+
+def copy_runs(src_ptr, dst_ptr, src_off, dst_off, nbytes, stream, use_batch=True):
+    """Batched DMA of contiguous runs; ``src_off``/``dst_off``/``nbytes`` are int64 numpy arrays
+    (bytes) that must stay alive until the call returns."""
+    import numpy as np
+    src_off = np.ascontiguousarray(src_off, dtype=np.int64)
+    dst_off = np.ascontiguousarray(dst_off, dtype=np.int64)
+    nbytes = np.ascontiguousarray(nbytes, dtype=np.int64)
+    if not (src_off.size == dst_off.size == nbytes.size):
+        raise ValueError('src_off, dst_off and nbytes must have the same length')
+    check(load_library().b200remap_copy_runs(
+        ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr),
+        ctypes.c_void_p(src_off.ctypes.data), ctypes.c_void_p(dst_off.ctypes.data),
+        ctypes.c_void_p(nbytes.ctypes.data), int(src_off.size), 1 if use_batch else 0,
         ctypes.c_void_p(stream) if stream else None))

@@ -335,12 +335,31 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     # which source rows travel: everything, a few contiguous runs (pageable memory), or -- when
     # the field sits in pinned memory the GPU can read directly -- exactly the touched rows
     rows_dev = None
+    dma = None
     row_bytes = lay.L * host.element_size()
-    zero_copy = host.is_pinned() and row_bytes % 16 == 0 and host.data_ptr() % 16 == 0
-    cov = matrix.cover_exact() if zero_copy else matrix.cover()
+    pinned = host.is_pinned()
+    zero_copy = pinned and row_bytes % 16 == 0 and host.data_ptr() % 16 == 0
+    cov = matrix.cover_exact() if pinned else matrix.cover()
+    if pinned and cov is not None:
+        # pinned input, exactly the touched rows.  Few long contiguous runs: one batched DMA
+        # submission per slice (copy engines run at full rate beside the D2H of results; SM loads
+        # from host memory do not: 4.3 vs 6.3 ms per C3 slice pair).  Many short runs: the GPU
+        # gathers the rows itself.
+        import os
+        n_runs = int(cov['run_start'].size)
+        want = os.environ.get('B200REMAP_H2D', 'auto')       # 'dma' | 'gather' | 'auto' (experiments)
+        if want == 'dma' or (want == 'auto' and n_runs <= 16384
+                             and cov['n_cover'] * row_bytes >= n_runs * 32768):
+            dma = (cov['run_start'] * row_bytes, cov['run_pos'] * row_bytes,
+                   cov['run_len'] * row_bytes)
+        elif not zero_copy:
+            cov = matrix.cover()
     if cov is None:
         csr = matrix.on_device(device.index)
         runs, n_x = [(0, lay.n_src, 0)], lay.n_src
+    elif dma is not None:
+        csr = matrix.on_device_cover(device.index, exact=True)
+        runs, n_x = None, cov['n_cover']
     elif zero_copy:
         csr = matrix.on_device_cover(device.index, exact=True)
         runs, n_x = None, cov['n_cover']
@@ -374,7 +393,10 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             if x_free[i] is not None:
                 s_in.wait_event(x_free[i])
             with torch.cuda.stream(s_in):
-                if rows_dev is not None:
+                if dma is not None:
+                    _cabi.copy_runs(src[b].data_ptr(), xd[i].data_ptr(), dma[0], dma[1], dma[2],
+                                    s_in.cuda_stream)
+                elif rows_dev is not None:
                     _cabi.gather_rows(src[b].data_ptr(), xd[i].data_ptr(), rows_dev.data_ptr(), n_x,
                                       row_bytes, row_bytes, s_in.cuda_stream)
                 else:

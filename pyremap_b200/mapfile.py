@@ -230,9 +230,16 @@ class WeightMatrix:
         self._cover_exact = None
         touched = np.unique(self.indices)
         if touched.size and touched.size <= worthwhile * self.shape[1]:
+            # the touched rows as maximal contiguous runs (start row, length, position)
+            split = np.nonzero(np.diff(touched) > 1)[0]
+            starts = np.concatenate([[touched[0]], touched[split + 1]]).astype(np.int64)
+            ends = np.concatenate([touched[split], [touched[-1]]]).astype(np.int64) + 1
+            lengths = ends - starts
+            positions = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
             self._cover_exact = {
                 'rows': touched.astype(np.int32), 'n_cover': int(touched.size),
-                'indices': np.searchsorted(touched, self.indices).astype(np.int32)}
+                'indices': np.searchsorted(touched, self.indices).astype(np.int32),
+                'run_start': starts, 'run_len': lengths, 'run_pos': positions}
         return self._cover_exact
 
     def on_device_cover(self, device=0, exact=False):

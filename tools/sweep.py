@@ -96,7 +96,7 @@ def sweep_c3(args):
             for kern, threads, pol, maxn in variants:
                 for which, v in ((0, threads), (1, pol), (5, maxn)):
                     _cabi.set_tunable(which, v if kern not in (4, 5) else 0)
-                _cabi.set_tunable(2, threads if kern in (4, 5, 8) else 0)    # staged kernels: stage cap
+                _cabi.set_tunable(2, threads if kern in (4, 5) else 0)    # staged kernels: stage cap
                 ms, best = time_launch(lambda i: run_spmm(csr, ring, y, K, nb, mode, i, kern))
                 report(f'{tag} x{nb}', f'kernel={kern} thr={threads} pol={pol} maxn={maxn}',
                        ms, best, nbytes)
@@ -131,12 +131,12 @@ def sweep_c2(args):
     ring = make_ring(m.n_a, 60, 12, True)
     y = torch.empty((12, m.n_b, 60), dtype=torch.float64, device='cuda')
     nbytes = alg_bytes(csr, 720)
-    for kern in (6, 7, 8, 3, 1):
+    for kern in (6, 7, 3, 1):
         ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, kern))
         report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern}', ms, best, nbytes)
     flat = ring.permute(1, 0, 2).reshape(1, m.n_a, 720).contiguous()
     y2 = torch.empty((1, m.n_b, 720), dtype=torch.float64, device='cuda')
-    for kern, maxn in ((0, 0), (6, 0), (7, 0), (8, 0), (3, 6), (1, 0)):
+    for kern, maxn in ((0, 0), (6, 0), (7, 0), (3, 6), (1, 0)):
         _cabi.set_tunable(5, maxn)
         ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, kern))
         report('C2 masked [nCells,720]', f'flat K=720 kernel={kern} maxn={maxn}', ms, best, nbytes)
