@@ -1,0 +1,14 @@
+#!/bin/bash
+# GPU session 15: full parity suite, smoke, bench (WROW default for batched masked sweeps, DMA-runs
+# e2e), reference arm, ncu launch list + full capture of the dominant kernel of the bench command
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+( time timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err ) 2>&1 | tail -3; tail -c 3800 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 600 gpurun_out/bench_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --slices 64 --no-e2e --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wrow_kernel -s 12 -c 1 -o gpurun_out/prof_bench_wrow -f python bench.py --steps 1 --warmup 1 --slices 64 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out
