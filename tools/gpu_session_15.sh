@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session 15: full parity suite, smoke, bench (WROW default for batched masked sweeps, DMA-runs
+# GPU session 15/17: full parity suite, smoke, bench (WROW default for batched masked sweeps, DMA-runs
 # e2e), reference arm, ncu launch list + full capture of the dominant kernel of the bench command
 set -x
 mkdir -p gpurun_out
