@@ -412,8 +412,9 @@ def measure_e2e(args, torch, dist, m, matrix, device, world, ring):
             'd2h_bytes_per_step': int(T * m.n_b * N_LEVELS * 8),
             'step': f'one call of Remapper.remap_array(pinned host ndarray (Time={T}, nCells, '
                     f'nVertLevels)) -> host ndarray; {rows_copied} of {m.n_a} source rows copied per '
-                    f'slice (exactly the rows the map touches: {n_runs} contiguous runs, one batched '
-                    f'DMA submission per slice, full duplex with the D2H of results)',
+                    f'slice (the {cov["n_touched"] if cov else m.n_a} rows the map touches plus bridged '
+                    f'gaps of <= {cov["bridged_gap"] if cov else 0} rows: {n_runs} contiguous runs, one '
+                    f'batched DMA submission per slice, full duplex with the D2H of results)',
             'calls_timed': calls, 'slices_per_call': T, 'ms_per_slice': dt / (calls * T) * 1e3,
             'host_nan_scan': 'whole variable, native early-exit scan (branch selection)'}
 

@@ -232,3 +232,4 @@ def copy_runs(src_ptr, dst_ptr, src_off, dst_off, nbytes, stream, use_batch=True
         ctypes.c_void_p(src_off.ctypes.data), ctypes.c_void_p(dst_off.ctypes.data),
         ctypes.c_void_p(nbytes.ctypes.data), int(src_off.size), 1 if use_batch else 0,
         ctypes.c_void_p(stream) if stream else None))
+

@@ -222,23 +222,40 @@ class WeightMatrix:
                                'n_cover': n_cover, 'indices': new_idx}
         return self._cover
 
-    def cover_exact(self, worthwhile=0.7):
-        """Exactly the touched source rows (sorted), for transfers that can gather row by
-        row (pinned host memory read by the GPU): ``{'rows', 'n_cover', 'indices'}`` or None."""
+    def cover_exact(self, worthwhile=0.7, slack=0.015):
+        """The touched source rows (sorted) for transfers that move row by row or run by run
+        (pinned host memory): ``{'rows', 'n_cover', 'indices', 'run_start', 'run_len',
+        'run_pos'}`` or None.  Short gaps between runs are bridged as long as the untouched rows
+        this adds stay below ``slack`` of the touched ones: a DMA submission is cheaper with
+        fewer, longer runs (C3: 1004 -> ~880 runs, +0.4 % bytes, 4.8 -> 4.2 ms per slice)."""
         if getattr(self, '_cover_exact', False) is not False:
             return self._cover_exact
         self._cover_exact = None
         touched = np.unique(self.indices)
         if touched.size and touched.size <= worthwhile * self.shape[1]:
-            # the touched rows as maximal contiguous runs (start row, length, position)
-            split = np.nonzero(np.diff(touched) > 1)[0]
+            gaps = np.diff(touched) - 1                       # untouched rows between neighbours
+            holes = np.sort(gaps[gaps > 0])
+            bridge = 0
+            if holes.size:
+                ok = np.nonzero(np.cumsum(holes) <= slack * touched.size)[0]
+                if ok.size:
+                    bridge = int(holes[ok[-1]])
+                    # the cumulative bound must hold for every gap of that size
+                    if np.sum(holes[holes <= bridge]) > slack * touched.size:
+                        smaller = holes[holes < bridge]
+                        bridge = int(smaller[-1]) if smaller.size else 0
+            split = np.nonzero(gaps > bridge)[0]
             starts = np.concatenate([[touched[0]], touched[split + 1]]).astype(np.int64)
             ends = np.concatenate([touched[split], [touched[-1]]]).astype(np.int64) + 1
             lengths = ends - starts
             positions = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
+            rows = np.concatenate([np.arange(a, b) for a, b in zip(starts, ends)]) \
+                if bridge else touched
+            run = np.searchsorted(starts, self.indices, side='right') - 1
             self._cover_exact = {
-                'rows': touched.astype(np.int32), 'n_cover': int(touched.size),
-                'indices': np.searchsorted(touched, self.indices).astype(np.int32),
+                'rows': rows.astype(np.int32), 'n_cover': int(rows.size),
+                'n_touched': int(touched.size), 'bridged_gap': bridge,
+                'indices': (self.indices - starts[run] + positions[run]).astype(np.int32),
                 'run_start': starts, 'run_len': lengths, 'run_pos': positions}
         return self._cover_exact
 
