@@ -35,8 +35,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_LEVELS = 80
-RING = 8                     # distinct slices resident in HBM
-BATCH = 8                    # slices per fused launch (Time chunk)
+RING = int(os.environ.get('B200REMAP_BENCH_RING', '8'))     # distinct slices resident in HBM
+BATCH = int(os.environ.get('B200REMAP_BENCH_BATCH', '8'))   # slices per fused launch (Time chunk)
 THRESHOLD = 0.01
 METRIC = 'remap_field_slices_per_s'
 UNIT = 'field-slices/s'
