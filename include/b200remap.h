@@ -110,6 +110,17 @@ B200REMAP_API int b200remap_spmm(const b200remap_csr *csr, const void *X, int x_
                    int64_t y_batch_stride, uint8_t *keep_out, int mode,
                    double threshold, int kernel, void *cuda_stream);
 
+/* The same product with a float32 result: every element is the float64 value b200remap_spmm
+ * writes, rounded to nearest float32 (so it equals numpy's `.astype(float32)` of the reference's
+ * result bit for bit; NaN placement unchanged).  Halves the output traffic for float32 workflows
+ * (SURVEY §8f rank 3).  Y strides are in float32 elements.  Not offered by the ROWBLOCK / TMA /
+ * STAGED kernel selectors. */
+B200REMAP_API int b200remap_spmm_f32out(const b200remap_csr *csr, const void *X, int x_dtype,
+                   int64_t K, int64_t ldx, int64_t nbatch, int64_t x_batch_stride,
+                   const uint8_t *valid, float *Y, int64_t ldy, int64_t y_batch_stride,
+                   uint8_t *keep_out, int mode, double threshold, int kernel,
+                   void *cuda_stream);
+
 /* *flag_dev (device int32) := 1 if any of the n elements of X is NaN, else 0.
  * Blocks stop reading as soon as a NaN has been seen anywhere. */
 B200REMAP_API int b200remap_any_nan(const void *X, int x_dtype, int64_t n, int32_t *flag_dev,

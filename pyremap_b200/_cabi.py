@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
+    'b200remap_spmm_f32out',
 )
 
 
@@ -83,6 +84,7 @@ def load_library():
         lib.b200remap_csr_info.argtypes = [vp, ctypes.POINTER(i64)]
         lib.b200remap_spmm.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp,
                                        i64, i64, vp, i32, dbl, i32, vp]
+        lib.b200remap_spmm_f32out.argtypes = lib.b200remap_spmm.argtypes
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
@@ -95,7 +97,8 @@ def load_library():
                      'b200remap_spmm', 'b200remap_any_nan',
                      'b200remap_transpose', 'b200remap_set_tunable',
                      'b200remap_debug_divide', 'b200remap_host_any_nan',
-                     'b200remap_gather_rows', 'b200remap_copy_runs'):
+                     'b200remap_gather_rows', 'b200remap_copy_runs',
+                     'b200remap_spmm_f32out'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -162,11 +165,13 @@ class DeviceCSR:
 
     def spmm(self, x_ptr, x_dtype, K, ldx, nbatch, x_batch_stride, y_ptr, ldy,
              y_batch_stride, mode, threshold=0.0, valid_ptr=None,
-             keep_ptr=None, kernel=KERNEL_AUTO, stream=0):
-        """Raw pointer-level call of ``b200remap_spmm`` (asynchronous)."""
+             keep_ptr=None, kernel=KERNEL_AUTO, stream=0, y_f32=False):
+        """Raw pointer-level call of ``b200remap_spmm`` (asynchronous); ``y_f32``: the result
+        buffer holds float32 (``b200remap_spmm_f32out``)."""
         if not self._handle:
             raise B200RemapError(-1, 'DeviceCSR is closed')
-        check(self._lib.b200remap_spmm(
+        fn = self._lib.b200remap_spmm_f32out if y_f32 else self._lib.b200remap_spmm
+        check(fn(
             self._handle, ctypes.c_void_p(x_ptr), int(x_dtype), int(K), int(ldx),
             int(nbatch), int(x_batch_stride),
             ctypes.c_void_p(valid_ptr) if valid_ptr else None,

@@ -110,6 +110,18 @@ def _as_device_tensor(array, device, torch):
     return t.to(device, non_blocking=True)
 
 
+def _wants_f32(out_dtype):
+    if out_dtype is None:
+        return False
+    dt = np.dtype(out_dtype) if not str(out_dtype).startswith('torch.') else \
+        np.dtype(str(out_dtype).split('.')[1])
+    if dt == np.float64:
+        return False
+    if dt == np.float32:
+        return True
+    raise ValueError(f'out_dtype must be float64 or float32, got {out_dtype}')
+
+
 def _dtype_code(t, torch):
     return F64 if t.dtype == torch.float64 else F32
 
@@ -136,7 +148,7 @@ def _transpose2d(t, nbatch, rows, cols, torch):
 
 def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                   valid=None, mode='auto', device=None, want_keep=False,
-                  return_torch=False, kernel=KERNEL_AUTO):
+                  return_torch=False, kernel=KERNEL_AUTO, out_dtype=None):
     """Remap ``field`` and return the NaN-filled float64 result.
 
     Parameters
@@ -155,12 +167,16 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
         field has a mask (explicit, or any NaN anywhere), else ``frac_b``.
     want_keep : also return the boolean keep mask (``~`` of the reference's
         output mask).
+    out_dtype : ``None`` / ``float64`` (the reference's result type) or ``float32``: every
+        element is then the float64 result rounded to nearest float32 (= the reference's
+        result ``.astype(float32)``), written by the kernel itself -- half the output traffic.
 
     Returns ``out`` or ``(out, keep)``; numpy arrays unless ``return_torch``.
     """
     torch = _torch()
     device = require_cuda(device if device is not None else (
         field.device if isinstance(field, torch.Tensor) and field.is_cuda else None))
+    y_f32 = _wants_f32(out_dtype)
     lay = Layout(field.shape, remap_axes, dst_dims)
     if lay.n_src != matrix.shape[1]:
         raise ValueError(f'field has {lay.n_src} source cells but the map has '
@@ -172,7 +188,8 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
             and not (lay.L == 1 and lay.B > 1) and lay.L > 0 and lay.n_dst > 0):
         host = _host_view(field, torch)
         if host is not None:
-            return _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch)
+            return _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch,
+                                        y_f32)
     csr = matrix.on_device(device.index)
 
     with torch.cuda.device(device):
@@ -224,7 +241,8 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                 1, lay.n_src, lay.K).contiguous()
             B, L = 1, lay.K
 
-        y3 = torch.empty((B, lay.n_dst, L), dtype=torch.float64, device=device)
+        y3 = torch.empty((B, lay.n_dst, L), dtype=torch.float32 if y_f32 else torch.float64,
+                         device=device)
         k3 = torch.empty((B, lay.n_dst, L), dtype=torch.uint8,
                          device=device) if want_keep else None
         if L > 0 and lay.n_dst > 0:
@@ -235,7 +253,7 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                          mode_code, thr,
                          valid_ptr=None if v3 is None else v3[b0].data_ptr(),
                          keep_ptr=None if k3 is None else k3[b0].data_ptr(),
-                         kernel=kernel, stream=stream.cuda_stream)
+                         kernel=kernel, stream=stream.cuda_stream, y_f32=y_f32)
 
         # ---- back to the caller's layout (remap_numpy.py:280-295) ----
         def restore(t3):
@@ -309,7 +327,7 @@ def _host_view(field, torch):
     return torch.from_numpy(a)
 
 
-def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch):
+def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch, y_f32=False):
     """Host field in, host result out, one fused launch per leading-axis slice.
 
     * branch selection over the whole variable on the host (native early-exit scan),
@@ -380,10 +398,11 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
         compute = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device, torch)
         trace.mark('weights on device')
-        out = torch.empty((B, lay.n_dst, L), dtype=torch.float64, pin_memory=True)
+        y_dtype = torch.float32 if y_f32 else torch.float64
+        out = torch.empty((B, lay.n_dst, L), dtype=y_dtype, pin_memory=True)
         nbuf = min(2, B)
         xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
-        yd = [torch.empty((lay.n_dst, L), dtype=torch.float64, device=device) for _ in range(nbuf)]
+        yd = [torch.empty((lay.n_dst, L), dtype=y_dtype, device=device) for _ in range(nbuf)]
         trace.mark('buffers')
         x_free = [None] * nbuf      # kernel that last read xd[i] has finished
         y_free = [None] * nbuf      # D2H that last read yd[i] has finished
@@ -409,7 +428,7 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             if y_free[i] is not None:
                 compute.wait_event(y_free[i])
             csr.spmm(xd[i].data_ptr(), code, L, L, 1, 0, yd[i].data_ptr(), L, 0, mode_code, thr,
-                     kernel=kernel, stream=compute.cuda_stream)
+                     kernel=kernel, stream=compute.cuda_stream, y_f32=y_f32)
             done = torch.cuda.Event()
             done.record(compute)
             x_free[i] = done

@@ -223,14 +223,17 @@ def _remap_numpy_array(remapper, in_field, remap_axes,
 
 
 def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
-                return_torch=False):
+                return_torch=False, out_dtype=None):
     """NaN-filled remap of a plain array or CUDA tensor (new, not in the
     reference): what ``_remap_data_array`` computes for ``da.values``, i.e.
-    ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch."""
+    ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch.
+    ``out_dtype=np.float32`` returns that float64 result rounded to float32
+    (the reference always returns float64, which stays the default)."""
     if remapper.map_filename is None and remapper._matrix is None:
         raise ValueError('No mapping file has been defined')
     _load_mapping(remapper)
     return engine.apply_weights(
         remapper._matrix, _dst_dims(remapper), field, list(remap_axes),
         renormalization_threshold, mode='auto',
-        device=getattr(remapper, 'device', None), return_torch=return_torch)
+        device=getattr(remapper, 'device', None), return_torch=return_torch,
+        out_dtype=out_dtype)

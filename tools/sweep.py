@@ -29,8 +29,8 @@ def device_csr(m):
     return mapfile.WeightMatrix(ip, ix, d, (m.n_b, m.n_a), m.frac_b).on_device(0)
 
 
-def alg_bytes(csr, K, w=8):
-    return csr.nnz * 12 + (csr.n_row + 1) * 4 + csr.n_touched * K * w + csr.n_row * K * 8
+def alg_bytes(csr, K, w=8, w_out=8):
+    return csr.nnz * 12 + (csr.n_row + 1) * 4 + csr.n_touched * K * w + csr.n_row * K * w_out
 
 
 def time_launch(fn, reps=10, warm=3):
@@ -69,7 +69,8 @@ def run_spmm(csr, ring, y, K, nb, mode, i, kernel=0):
     base = ((i * nb) % n) if nb < n else 0
     code = _cabi.F64 if ring.dtype == torch.float64 else _cabi.F32
     csr.spmm(ring[base].data_ptr(), code, K, K, nb, ring.shape[1] * K, y.data_ptr(), K,
-             csr.n_row * K, mode, 0.01, kernel=kernel, stream=st)
+             csr.n_row * K, mode, 0.01, kernel=kernel, stream=st,
+             y_f32=y.dtype == torch.float32)
 
 
 def sweep_c3(args):
@@ -108,6 +109,12 @@ def sweep_c3(args):
             nbytes = alg_bytes(csr, K, 4) * 4
             ms, best = time_launch(lambda i: run_spmm(csr, ring32, y, K, 4, mode, i, 0))
             report('C3 masked f32-in x4', 'default', ms, best, nbytes)
+            y32 = torch.empty((8, m.n_b, K), dtype=torch.float32, device='cuda')
+            ms, best = time_launch(lambda i: run_spmm(csr, ring32, y32, K, 4, mode, i, 0))
+            report('C3 masked f32-in f32-out x4', 'default', ms, best, alg_bytes(csr, K, 4, 4) * 4)
+            ms, best = time_launch(lambda i: run_spmm(csr, ring, y32, K, 8, mode, i, 0))
+            report('C3 masked f64-in f32-out x8', 'default', ms, best, alg_bytes(csr, K, 8, 4) * 8)
+            del y32
             del ring32
         del ring
     # any-NaN scan over a NaN-free slice (worst case: no early exit) and a masked one
