@@ -382,7 +382,9 @@ def measure_e2e(args, torch, dist, m, matrix, device, world, ring):
     r._matrix = matrix
     r._ds_map = mapfile_dataset(m)
     r.device = device.index
-    T = max(1, min(args.e2e_slices, RING))
+    # every rank pins T input slices (2.36 GB each) plus its results: keep the host footprint of
+    # an 8-rank run moderate (4 slices per call there, 8 on 1-2 GPUs)
+    T = max(1, min(args.e2e_slices if world <= 2 else min(args.e2e_slices, 4), RING))
     host_t = torch.empty((T, m.n_a, N_LEVELS), dtype=torch.float64, pin_memory=True)
     host_t.copy_(ring[:T])                      # same synthetic slices, now in host memory
     torch.cuda.synchronize(device)
