@@ -64,7 +64,9 @@ extern "C" {
                                     Y = den > threshold ? num/den : NaN
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
-/* kernel selection (0 = let the library choose from K and the row-length profile) */
+/* kernel selection (0 = let the library choose: rows longer than 8 entries on average ->
+ * LANES_K; masked branch with >= 2 slices per call -> WROW, in launches of at most 8 slices;
+ * otherwise PBIN) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
