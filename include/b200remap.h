@@ -159,6 +159,17 @@ B200REMAP_API int b200remap_copy_runs(const void *src, void *dst, const int64_t 
                         const int64_t *dst_off, const int64_t *bytes, int64_t n_runs,
                         int use_batch, void *cuda_stream);
 
+/* Map loader on the GPU: 0-based COO triplets -> the canonical CSR that
+ * `csr_matrix((S, (row, col)), shape=(n_row, n_col))` builds in _load_mapping
+ * (remap_numpy.py:134-137): rows in order, columns sorted within a row, duplicates of one
+ * (row, col) summed left to right in file order.  row/col/S are host pointers unless
+ * ptrs_are_device; indptr_dev[n_row+1], indices_dev[n_s], data_dev[n_s] are caller-owned DEVICE
+ * buffers (the first *nnz_out entries of indices/data are valid).  Synchronises the stream. */
+B200REMAP_API int b200remap_coo_to_csr(int device, int64_t n_row, int64_t n_col, int64_t n_s,
+                         const int32_t *row, const int32_t *col, const double *S,
+                         int ptrs_are_device, int32_t *indptr_dev, int32_t *indices_dev,
+                         double *data_dev, int64_t *nnz_out, void *cuda_stream);
+
 /* diagnostic: q[i] = a[i] / b[i] (device pointers) through the library's shared-reciprocal
  * division, which must equal IEEE-754 division bit for bit (pinned by the test-suite) */
 B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, double *q, int64_t n,

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
-    'b200remap_spmm_f32out',
+    'b200remap_spmm_f32out', 'b200remap_coo_to_csr',
 )
 
 
@@ -85,6 +85,8 @@ def load_library():
         lib.b200remap_spmm.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp,
                                        i64, i64, vp, i32, dbl, i32, vp]
         lib.b200remap_spmm_f32out.argtypes = lib.b200remap_spmm.argtypes
+        lib.b200remap_coo_to_csr.argtypes = [i32, i64, i64, i64, vp, vp, vp, i32, vp, vp, vp,
+                                             ctypes.POINTER(i64), vp]
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
@@ -98,7 +100,7 @@ def load_library():
                      'b200remap_transpose', 'b200remap_set_tunable',
                      'b200remap_debug_divide', 'b200remap_host_any_nan',
                      'b200remap_gather_rows', 'b200remap_copy_runs',
-                     'b200remap_spmm_f32out'):
+                     'b200remap_spmm_f32out', 'b200remap_coo_to_csr'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -238,3 +240,16 @@ def copy_runs(src_ptr, dst_ptr, src_off, dst_off, nbytes, stream, use_batch=True
         ctypes.c_void_p(nbytes.ctypes.data), int(src_off.size), 1 if use_batch else 0,
         ctypes.c_void_p(stream) if stream else None))
 
+
+
+def coo_to_csr_device(device, n_row, n_col, row, col, S, indptr_ptr, indices_ptr, data_ptr, stream=0):
+    """``b200remap_coo_to_csr`` on host triplets (int32 row/col 0-based, float64 S, numpy);
+    the three output pointers are device buffers of n_row+1 / n_s / n_s elements.  Returns nnz."""
+    nnz = ctypes.c_int64(0)
+    check(load_library().b200remap_coo_to_csr(
+        int(device), int(n_row), int(n_col), int(S.size),
+        ctypes.c_void_p(row.ctypes.data), ctypes.c_void_p(col.ctypes.data),
+        ctypes.c_void_p(S.ctypes.data), 0, ctypes.c_void_p(indptr_ptr),
+        ctypes.c_void_p(indices_ptr), ctypes.c_void_p(data_ptr), ctypes.byref(nnz),
+        ctypes.c_void_p(stream) if stream else None))
+    return int(nnz.value)

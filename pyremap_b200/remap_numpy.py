@@ -30,7 +30,18 @@ import sys
 import numpy as np
 
 from . import engine
-from .mapfile import WeightMatrix, coo_to_csr, open_map
+from .mapfile import WeightMatrix, coo_to_csr, coo_to_csr_gpu, open_map
+
+
+_GPU_CSR_MIN_WEIGHTS = 1 << 21
+
+
+def _cuda_ready():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except ImportError:
+        return False
 
 
 def _xr():
@@ -134,7 +145,13 @@ def _load_mapping(remapper):
     col = np.asarray(ds_map['col'].values).astype(np.int64) - 1
     row = np.asarray(ds_map['row'].values).astype(np.int64) - 1
     s = ds_map['S'].values
-    indptr, indices, data = coo_to_csr(s, row, col, n_b, n_a)
+    # large maps are sorted on the GPU (bit-identical, tests/test_gpu_parity.py); small ones and
+    # machines that only inspect a map (no device) use the NumPy builder
+    if np.size(s) >= _GPU_CSR_MIN_WEIGHTS and _cuda_ready():
+        indptr, indices, data = coo_to_csr_gpu(s, row, col, n_b, n_a,
+                                               getattr(remapper, 'device', None) or 0)
+    else:
+        indptr, indices, data = coo_to_csr(s, row, col, n_b, n_a)
     frac_b = np.asarray(ds_map['frac_b'].values, dtype=np.float64)
     remapper._matrix = WeightMatrix(indptr, indices, data, (n_b, n_a), frac_b)
     remapper._ds_map = ds_map
