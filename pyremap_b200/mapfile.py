@@ -219,6 +219,14 @@ class WeightMatrix:
                                              self.shape[1], device)
         return self._device[device]
 
+    def _touched_rows(self):
+        """Sorted distinct source rows the map references (O(nnz), no sort)."""
+        if getattr(self, '_touched', None) is None:
+            seen = np.zeros(self.shape[1], dtype=bool)
+            seen[self.indices] = True
+            self._touched = np.flatnonzero(seen)
+        return self._touched
+
     def cover(self, max_runs=64, worthwhile=0.7):
         """Source rows a host->device copy has to bring over, as a few contiguous runs.
 
@@ -233,7 +241,7 @@ class WeightMatrix:
             return self._cover
         self._cover = None
         n_a = self.shape[1]
-        touched = np.unique(self.indices)
+        touched = self._touched_rows()
         if touched.size and touched.size <= worthwhile * n_a:
             gaps = np.diff(touched) - 1
             cut = 0
@@ -262,7 +270,7 @@ class WeightMatrix:
         if getattr(self, '_cover_exact', False) is not False:
             return self._cover_exact
         self._cover_exact = None
-        touched = np.unique(self.indices)
+        touched = self._touched_rows()
         if touched.size and touched.size <= worthwhile * self.shape[1]:
             gaps = np.diff(touched) - 1                       # untouched rows between neighbours
             holes = np.sort(gaps[gaps > 0])
