@@ -159,6 +159,14 @@ B200REMAP_API int b200remap_copy_runs(const void *src, void *dst, const int64_t 
                         const int64_t *dst_off, const int64_t *bytes, int64_t n_runs,
                         int use_batch, void *cuda_stream);
 
+/* The same runs copied by CPU threads between two HOST buffers: packs the touched source-row
+ * runs of a slice that lives in pageable memory into one pinned staging block, which then
+ * crosses PCIe as a single DMA (pageable memory cannot be read by the copy engines directly;
+ * a plain cudaMemcpy of the bridged runs moved 417 MB per C3 slice at ~10 GB/s). */
+B200REMAP_API int b200remap_host_pack_runs(const void *src, void *dst, const int64_t *src_off,
+                             const int64_t *dst_off, const int64_t *bytes, int64_t n_runs,
+                             int threads);
+
 /* Map loader on the GPU: 0-based COO triplets -> the canonical CSR that
  * `csr_matrix((S, (row, col)), shape=(n_row, n_col))` builds in _load_mapping
  * (remap_numpy.py:134-137): rows in order, columns sorted within a row, duplicates of one

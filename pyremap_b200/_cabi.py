@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_csr_info', 'b200remap_spmm', 'b200remap_any_nan',
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
-    'b200remap_spmm_f32out', 'b200remap_coo_to_csr',
+    'b200remap_spmm_f32out', 'b200remap_coo_to_csr', 'b200remap_host_pack_runs',
 )
 
 
@@ -87,6 +87,7 @@ def load_library():
         lib.b200remap_spmm_f32out.argtypes = lib.b200remap_spmm.argtypes
         lib.b200remap_coo_to_csr.argtypes = [i32, i64, i64, i64, vp, vp, vp, i32, vp, vp, vp,
                                              ctypes.POINTER(i64), vp]
+        lib.b200remap_host_pack_runs.argtypes = [vp, vp, vp, vp, vp, i64, i32]
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
@@ -100,7 +101,8 @@ def load_library():
                      'b200remap_transpose', 'b200remap_set_tunable',
                      'b200remap_debug_divide', 'b200remap_host_any_nan',
                      'b200remap_gather_rows', 'b200remap_copy_runs',
-                     'b200remap_spmm_f32out', 'b200remap_coo_to_csr'):
+                     'b200remap_spmm_f32out', 'b200remap_coo_to_csr',
+                     'b200remap_host_pack_runs'):
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
@@ -253,3 +255,12 @@ def coo_to_csr_device(device, n_row, n_col, row, col, S, indptr_ptr, indices_ptr
         ctypes.c_void_p(indices_ptr), ctypes.c_void_p(data_ptr), ctypes.byref(nnz),
         ctypes.c_void_p(stream) if stream else None))
     return int(nnz.value)
+
+
+def host_pack_runs(src_ptr, dst_ptr, src_off, dst_off, nbytes, threads=8):
+    """CPU-thread packing of runs between two host buffers (offsets / sizes: int64 numpy, bytes);
+    releases the GIL for the duration of the call."""
+    check(load_library().b200remap_host_pack_runs(
+        ctypes.c_void_p(src_ptr), ctypes.c_void_p(dst_ptr),
+        ctypes.c_void_p(src_off.ctypes.data), ctypes.c_void_p(dst_off.ctypes.data),
+        ctypes.c_void_p(nbytes.ctypes.data), int(src_off.size), int(threads)))
