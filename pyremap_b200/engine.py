@@ -148,7 +148,7 @@ def _transpose2d(t, nbatch, rows, cols, torch):
 
 def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                   valid=None, mode='auto', device=None, want_keep=False,
-                  return_torch=False, kernel=KERNEL_AUTO, out_dtype=None):
+                  return_torch=False, kernel=KERNEL_AUTO, out_dtype=None, out=None):
     """Remap ``field`` and return the NaN-filled float64 result.
 
     Parameters
@@ -167,6 +167,9 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
         field has a mask (explicit, or any NaN anywhere), else ``frac_b``.
     want_keep : also return the boolean keep mask (``~`` of the reference's
         output mask).
+    out : optional preallocated HOST result (numpy array or CPU tensor, C-contiguous, shape of
+        the result, dtype ``out_dtype``) for host inputs: pinned memory receives the
+        device->host copies directly, other memory is filled through a pinned staging ring.
     out_dtype : ``None`` / ``float64`` (the reference's result type) or ``float32``: every
         element is then the float64 result rounded to nearest float32 (= the reference's
         result ``.astype(float32)``), written by the kernel itself -- half the output traffic.
@@ -189,7 +192,10 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
         host = _host_view(field, torch)
         if host is not None:
             return _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch,
-                                        y_f32)
+                                        y_f32, out)
+    if out is not None:
+        raise ValueError('out= is only supported for contiguous host arrays remapped along '
+                         'adjacent axes (the streamed path)')
     csr = matrix.on_device(device.index)
 
     with torch.cuda.device(device):
@@ -311,6 +317,35 @@ def _side_streams(device, torch):
     return _STREAMS[key]
 
 
+_PINNED = {}
+
+
+def _pinned_ring(torch, tag, count, nbytes):
+    """``count`` persistent pinned byte buffers of at least ``nbytes`` (per process, grown on
+    demand, never returned): page-locking fresh memory runs at ~2 GB/s, far below PCIe, so the
+    staging blocks of the streamed path are allocated once and reused by every call."""
+    ring = _PINNED.get(tag)
+    if ring is None or len(ring) < count or ring[0].numel() < nbytes:
+        ring = [torch.empty(max(int(nbytes), 1), dtype=torch.uint8, pin_memory=True)
+                for _ in range(count)]
+        _PINNED[tag] = ring
+    return ring
+
+
+def _chunks(nbytes, piece=1 << 20):
+    off = np.arange(0, max(int(nbytes), 1), piece, dtype=np.int64)
+    return off, np.minimum(piece, nbytes - off).astype(np.int64)
+
+
+def _host_out(out, shape, y_dtype, torch):
+    """Validate a caller-provided result buffer; returns it as a CPU tensor of ``shape``."""
+    t = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+    if t.is_cuda or t.dtype != y_dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f'out must be a C-contiguous host array of shape {tuple(shape)} and '
+                         f'dtype {y_dtype}')
+    return t
+
+
 def _host_view(field, torch):
     """A C-contiguous float32/float64 CPU tensor sharing ``field``'s memory, or None."""
     if isinstance(field, torch.Tensor):
@@ -327,7 +362,8 @@ def _host_view(field, torch):
     return torch.from_numpy(a)
 
 
-def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch, y_f32=False):
+def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch, y_f32=False,
+                         out=None):
     """Host field in, host result out, one fused launch per leading-axis slice.
 
     * branch selection over the whole variable on the host (native early-exit scan),
@@ -335,7 +371,11 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
       (regional maps: a few contiguous runs, :meth:`WeightMatrix.cover`);
     * per slice: H2D on a copy stream, kernel on the current stream, D2H into pinned
       memory on a second copy stream -- the three overlap across slices (PCIe is full
-      duplex) with double-buffered device tensors.
+      duplex) with double-buffered device tensors;
+    * the result: a caller-provided pinned ``out`` receives the D2H copies directly; otherwise
+      they land in a persistent pinned ring and CPU threads move each slice into a fresh
+      (pageable) array while the next slices are in flight -- page-locking a fresh result
+      block per call would cost ~0.5 ms per MB.
     """
     trace = _Trace()
     if mode == 'auto':
@@ -415,21 +455,42 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
         s_in, s_out = _side_streams(device, torch)
         trace.mark('weights on device')
         y_dtype = torch.float32 if y_f32 else torch.float64
-        out = torch.empty((B, lay.n_dst, L), dtype=y_dtype, pin_memory=True)
         nbuf = min(2, B)
+        import os
+        threads = max(1, min(8, os.cpu_count() or 1))
+        out_shape = (B, lay.n_dst, L)
+        out_t = torch.from_numpy(np.empty(out_shape, dtype=np.float32 if y_f32 else np.float64)) \
+            if out is None else _host_out(out, lay.out_shape, y_dtype, torch).view(out_shape)
+        direct = out_t.is_pinned()
+        slice_bytes = lay.n_dst * L * out_t.element_size()
+        if not direct:
+            ring_out = [r_[:slice_bytes].view(y_dtype).view(lay.n_dst, L)
+                        for r_ in _pinned_ring(torch, ('out', device.index), nbuf, slice_bytes)]
+            c_off, c_len = _chunks(slice_bytes)
+        pending = [None] * nbuf     # (slice index, D2H-finished event) parked in ring_out[i]
+
+        def drain(i):
+            if pending[i] is not None:
+                b_done, ev = pending[i]
+                ev.synchronize()
+                _cabi.host_pack_runs(ring_out[i].data_ptr(), out_t[b_done].data_ptr(), c_off, c_off,
+                                     c_len, threads)
+                pending[i] = None
         xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
         yd = [torch.empty((lay.n_dst, L), dtype=y_dtype, device=device) for _ in range(nbuf)]
-        stage, stage_free, pack_threads = None, [None] * nbuf, 1
+        stage, stage_free, pack_threads = None, [None] * nbuf, threads
         if pack is not None:
-            import os
-            stage = [torch.empty((n_x, L), dtype=src.dtype, pin_memory=True) for _ in range(nbuf)]
-            pack_threads = max(1, min(8, os.cpu_count() or 1))
+            in_bytes = n_x * row_bytes
+            stage = [r_[:in_bytes].view(src.dtype).view(n_x, L)
+                     for r_ in _pinned_ring(torch, ('in', device.index), nbuf, in_bytes)]
         trace.mark('buffers')
         x_free = [None] * nbuf      # kernel that last read xd[i] has finished
         y_free = [None] * nbuf      # D2H that last read yd[i] has finished
         s_in.wait_stream(compute)
         for b in range(B):
             i = b % nbuf
+            if not direct:
+                drain(i)                 # the slice parked in ring_out[i] moves to the result
             if pack is not None:
                 if stage_free[i] is not None:
                     stage_free[i].synchronize()          # the DMA of slice b-2 has read stage[i]
@@ -464,15 +525,20 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             x_free[i] = done
             s_out.wait_event(done)
             with torch.cuda.stream(s_out):
-                out[b].copy_(yd[i], non_blocking=True)
+                (out_t[b] if direct else ring_out[i]).copy_(yd[i], non_blocking=True)
                 fin = torch.cuda.Event()
                 fin.record(s_out)
             y_free[i] = fin
+            if not direct:
+                pending[i] = (b, fin)
         for t in xd + yd:            # the side streams still use these buffers
             t.record_stream(s_in)
             t.record_stream(s_out)
         trace.mark('enqueue')
+        if not direct:
+            for i in sorted(range(nbuf), key=lambda j: pending[j][0] if pending[j] else -1):
+                drain(i)
         s_out.synchronize()
         trace.mark('drain')
     trace.report(f'streamed remap B={B} L={L} rows_copied={n_x}')
-    return out.numpy().reshape(lay.out_shape)
+    return out_t.numpy().reshape(lay.out_shape) if out is None else out

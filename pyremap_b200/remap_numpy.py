@@ -240,7 +240,7 @@ def _remap_numpy_array(remapper, in_field, remap_axes,
 
 
 def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
-                return_torch=False, out_dtype=None):
+                return_torch=False, out_dtype=None, out=None):
     """NaN-filled remap of a plain array or CUDA tensor (new, not in the
     reference): what ``_remap_data_array`` computes for ``da.values``, i.e.
     ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch.
@@ -253,4 +253,4 @@ def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
         remapper._matrix, _dst_dims(remapper), field, list(remap_axes),
         renormalization_threshold, mode='auto',
         device=getattr(remapper, 'device', None), return_torch=return_torch,
-        out_dtype=out_dtype)
+        out_dtype=out_dtype, out=out)

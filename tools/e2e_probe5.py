@@ -32,3 +32,16 @@ for name, arr in (('pinned', pinned.numpy()), ('pageable', pageable)):
     print(f'{name}: remap_array(T={T}) {t:.1f} ms = {t / T:.2f} ms/slice', flush=True)
 os.environ['B200REMAP_TRACE'] = '1'
 r.remap_array(pageable, [1], 0.01)
+os.environ.pop('B200REMAP_TRACE', None)
+keep = []
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(3):
+    keep.append(r.remap_array(pinned.numpy(), [1], 0.01))
+torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3 * 1e3
+print(f'pinned input, results kept alive (fresh pinned result block per call): {dt:.1f} ms per call = {dt / T:.2f} ms/slice')
+t = timed(lambda: torch.empty((T, m.n_b, L), dtype=torch.float64, pin_memory=True), n=2)
+keep2 = [torch.empty((T, m.n_b, L), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+torch.cuda.synchronize(); t0 = time.perf_counter(); keep2.append(torch.empty((T, m.n_b, L), dtype=torch.float64, pin_memory=True)); dt = (time.perf_counter() - t0) * 1e3
+print(f'fresh pinned allocation of {T * m.n_b * L * 8 / 1e6:.0f} MB: {dt:.1f} ms')
+t0 = time.perf_counter(); z = np.empty((T, m.n_b, L)); z[...] = 0; dt = (time.perf_counter() - t0) * 1e3
+print(f'fresh pageable allocation + first touch of the same size: {dt:.1f} ms')
