@@ -332,6 +332,18 @@ def _pinned_ring(torch, tag, count, nbytes):
     return ring
 
 
+_POOL = []
+
+
+def _copy_pool():
+    """One helper thread that moves finished slices from the pinned ring into the result while
+    the calling thread packs / enqueues the next ones."""
+    if not _POOL:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL.append(ThreadPoolExecutor(max_workers=1, thread_name_prefix='b200remap-copy'))
+    return _POOL[0]
+
+
 def _chunks(nbytes, piece=1 << 20):
     off = np.arange(0, max(int(nbytes), 1), piece, dtype=np.int64)
     return off, np.minimum(piece, nbytes - off).astype(np.int64)
@@ -467,14 +479,16 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             ring_out = [r_[:slice_bytes].view(y_dtype).view(lay.n_dst, L)
                         for r_ in _pinned_ring(torch, ('out', device.index), nbuf, slice_bytes)]
             c_off, c_len = _chunks(slice_bytes)
-        pending = [None] * nbuf     # (slice index, D2H-finished event) parked in ring_out[i]
+        pending = [None] * nbuf     # copy-out job of the slice parked in ring_out[i]
+
+        def copy_out(i, b_done, ev):      # runs on the helper thread (both calls drop the GIL)
+            ev.synchronize()
+            _cabi.host_pack_runs(ring_out[i].data_ptr(), out_t[b_done].data_ptr(), c_off, c_off,
+                                 c_len, threads)
 
         def drain(i):
             if pending[i] is not None:
-                b_done, ev = pending[i]
-                ev.synchronize()
-                _cabi.host_pack_runs(ring_out[i].data_ptr(), out_t[b_done].data_ptr(), c_off, c_off,
-                                     c_len, threads)
+                pending[i].result()
                 pending[i] = None
         xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
         yd = [torch.empty((lay.n_dst, L), dtype=y_dtype, device=device) for _ in range(nbuf)]
@@ -489,8 +503,6 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
         s_in.wait_stream(compute)
         for b in range(B):
             i = b % nbuf
-            if not direct:
-                drain(i)                 # the slice parked in ring_out[i] moves to the result
             if pack is not None:
                 if stage_free[i] is not None:
                     stage_free[i].synchronize()          # the DMA of slice b-2 has read stage[i]
@@ -524,19 +536,21 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
             done.record(compute)
             x_free[i] = done
             s_out.wait_event(done)
+            if not direct:
+                drain(i)                 # the slice parked in ring_out[i] has reached the result
             with torch.cuda.stream(s_out):
                 (out_t[b] if direct else ring_out[i]).copy_(yd[i], non_blocking=True)
                 fin = torch.cuda.Event()
                 fin.record(s_out)
             y_free[i] = fin
             if not direct:
-                pending[i] = (b, fin)
+                pending[i] = _copy_pool().submit(copy_out, i, b, fin)
         for t in xd + yd:            # the side streams still use these buffers
             t.record_stream(s_in)
             t.record_stream(s_out)
         trace.mark('enqueue')
         if not direct:
-            for i in sorted(range(nbuf), key=lambda j: pending[j][0] if pending[j] else -1):
+            for i in range(nbuf):
                 drain(i)
         s_out.synchronize()
         trace.mark('drain')
