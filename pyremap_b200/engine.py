@@ -318,6 +318,14 @@ def _side_streams(device, torch):
 
 
 _PINNED = {}
+_STREAM_LOCKS = {}
+
+
+def _stream_lock(device):
+    """The streamed path of a device (side streams, pinned staging rings) serves one call at a
+    time; concurrent callers queue here."""
+    import threading
+    return _STREAM_LOCKS.setdefault(device.index, threading.Lock())
 
 
 def _pinned_ring(torch, tag, count, nbytes):
@@ -462,7 +470,7 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     B, L = lay.B, lay.L
     src = host.view(B, lay.n_src, L)
     code = _dtype_code(src, torch)
-    with torch.cuda.device(device):
+    with _stream_lock(device), torch.cuda.device(device):
         compute = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device, torch)
         trace.mark('weights on device')
