@@ -411,6 +411,14 @@ def measure_e2e(args, torch, dist, m, matrix, device, world, ring):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     assert out.shape == (T, m.dst_descriptor.dim_sizes[0], m.dst_descriptor.dim_sizes[1], N_LEVELS)
+    # the same call without out=: a fresh pageable result per call (what the xarray path returns)
+    fresh = r.remap_array(host, [1], thr)
+    torch.cuda.synchronize(device)
+    t1 = time.perf_counter()
+    fresh = r.remap_array(host, [1], thr)
+    torch.cuda.synchronize(device)
+    dt_fresh = time.perf_counter() - t1
+    assert fresh.shape == out.shape
     cov = matrix.cover_exact()                  # pinned input: exactly the touched rows travel
     rows_copied = cov['n_cover'] if cov else m.n_a
     n_runs = int(cov['run_start'].size) if cov else 1
@@ -423,6 +431,7 @@ def measure_e2e(args, torch, dist, m, matrix, device, world, ring):
                     f'gaps of <= {cov["bridged_gap"] if cov else 0} rows: {n_runs} contiguous runs, one '
                     f'batched DMA submission per slice, full duplex with the D2H of results)',
             'calls_timed': calls, 'slices_per_call': T, 'ms_per_slice': dt / (calls * T) * 1e3,
+            'fresh_pageable_result_ms_per_slice_this_rank': dt_fresh / T * 1e3,
             'host_nan_scan': 'whole variable, native early-exit scan (branch selection)'}
 
 
