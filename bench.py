@@ -210,7 +210,7 @@ def run_reference(args):
         'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': time.time() - t0,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=JSON_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------
@@ -366,7 +366,7 @@ def run_b200(args):
             rate, sample, _, _ = cpu_reference_slice_rate(m, args.mode, args.cpu_seconds)
             out['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port',
                                    'sample': sample, 'host_cores_available': os.cpu_count()}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -441,8 +441,21 @@ def mapfile_dataset(m):
                                'src_grid_dims': m.src_grid_dims}, {})
 
 
+JSON_OUT = sys.stdout
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: everything else that writes to file descriptor 1
+    (NCCL prints its version banner there when NCCL_DEBUG is set) goes to stderr."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
