@@ -256,3 +256,48 @@ def test_cover_renumbering_is_monotonic_and_complete():
     full = syn.make_c1(30.0, 15.0)
     ip, ix, d = mapfile.coo_to_csr(full.S, full.row - 1, full.col - 1, full.n_b, full.n_a)
     assert mapfile.WeightMatrix(ip, ix, d, (full.n_b, full.n_a), full.frac_b).cover() is None
+
+
+@pytest.mark.parametrize('slack', [0.0, 0.015, 0.2])
+def test_cover_exact_runs_bridge_short_gaps_only(slack):
+    """``cover_exact``: every referenced source row keeps its data under the renumbering, the
+    runs tile the covered rows in order, and bridging adds at most ``slack`` untouched rows."""
+    from pyremap_b200 import mapfile
+    rng = np.random.default_rng(5)
+    n_a, n_b = 5000, 300
+    # touched rows: a few dense bands with small holes, the rest of the mesh untouched
+    touched = np.unique(np.concatenate([np.arange(100, 400), np.arange(402, 600),
+                                        np.arange(640, 900), rng.integers(2000, 2300, 200)]))
+    rows = np.repeat(np.arange(n_b), 4)
+    cols = rng.choice(touched, size=rows.size)
+    cols[:touched.size] = touched                      # every touched row is referenced
+    ip, ix, d = mapfile.coo_to_csr(rng.normal(size=rows.size), rows, cols, n_b, n_a)
+    W = mapfile.WeightMatrix(ip, ix, d, (n_b, n_a), np.ones(n_b))
+    cov = W.cover_exact(slack=slack)
+    assert cov is not None and cov['n_touched'] == touched.size
+    np.testing.assert_array_equal(cov['rows'][cov['indices']], ix)       # renumbering is faithful
+    np.testing.assert_array_equal(np.unique(cov['rows']), cov['rows'])    # sorted, no repeats
+    assert cov['n_cover'] - cov['n_touched'] <= slack * cov['n_touched']
+    starts, lens, pos = cov['run_start'], cov['run_len'], cov['run_pos']
+    assert np.all(lens > 0) and np.all(starts[1:] > starts[:-1] + lens[:-1])   # disjoint, ordered
+    np.testing.assert_array_equal(pos, np.concatenate([[0], np.cumsum(lens)[:-1]]))
+    np.testing.assert_array_equal(np.concatenate([np.arange(s, s + n) for s, n in zip(starts, lens)]),
+                                  cov['rows'])
+    if slack == 0.0:
+        assert cov['bridged_gap'] == 0 and cov['n_cover'] == touched.size
+    # a map that touches (nearly) everything has no worthwhile cover
+    ip2, ix2, d2 = mapfile.coo_to_csr(np.ones(n_a), np.arange(n_a) % n_b, np.arange(n_a), n_b, n_a)
+    assert mapfile.WeightMatrix(ip2, ix2, d2, (n_b, n_a), np.ones(n_b)).cover_exact() is None
+
+
+def test_engine_host_helpers():
+    from pyremap_b200 import engine
+    assert engine._wants_f32(None) is False and engine._wants_f32(np.float64) is False
+    assert engine._wants_f32(np.float32) is True and engine._wants_f32('float32') is True
+    with pytest.raises(ValueError, match='out_dtype'):
+        engine._wants_f32(np.int16)
+    off, ln = engine._chunks(2 * (1 << 20) + 5)
+    np.testing.assert_array_equal(off, [0, 1 << 20, 2 << 20])
+    np.testing.assert_array_equal(ln, [1 << 20, 1 << 20, 5])
+    off, ln = engine._chunks(7, piece=4)
+    assert off.tolist() == [0, 4] and ln.tolist() == [4, 3]
