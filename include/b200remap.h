@@ -70,9 +70,8 @@ extern "C" {
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
-#define B200REMAP_KERNEL_BINNED   3  /* lanes across K, rows binned by entry count            */
-#define B200REMAP_KERNEL_TMA      4  /* persistent warp-specialised pipeline, TMA bulk gathers */
-#define B200REMAP_KERNEL_STAGED   5  /* same pipeline, 16-byte cp.async gathers                */
+/* 3, 4, 5: selectors of round-1 experiments (non-persistent binned kernel, TMA / cp.async staged
+ * pipelines); they lost to PBIN / WROW on B200 and were removed -- E_INVALID now */
 #define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
 #define B200REMAP_KERNEL_WROW     7  /* warp-autonomous persistent binned tiles, no CTA barrier */
 

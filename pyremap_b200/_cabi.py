@@ -15,8 +15,7 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-(KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_BINNED, KERNEL_TMA,
- KERNEL_STAGED, KERNEL_PBIN, KERNEL_WROW) = 0, 1, 2, 3, 4, 5, 6, 7
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_PBIN, KERNEL_WROW = 0, 1, 2, 6, 7
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -106,6 +105,10 @@ def load_library():
             getattr(lib, name).restype = i32
         if lib.b200remap_abi_version() != 1:
             raise B200RemapError(-2, 'ABI version mismatch')
+        # experiments: B200REMAP_TUNABLES="13=2,7=20" presets b200remap_set_tunable knobs
+        for item in filter(None, os.environ.get('B200REMAP_TUNABLES', '').split(',')):
+            which, _, value = item.partition('=')
+            lib.b200remap_set_tunable(int(which), int(value))
         _lib = lib
     return _lib
 

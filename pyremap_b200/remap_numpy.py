@@ -240,17 +240,20 @@ def _remap_numpy_array(remapper, in_field, remap_axes,
 
 
 def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
-                return_torch=False, out_dtype=None, out=None):
+                return_torch=False, out_dtype=None, out=None, mode='auto'):
     """NaN-filled remap of a plain array or CUDA tensor (new, not in the
     reference): what ``_remap_data_array`` computes for ``da.values``, i.e.
     ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch.
     ``out_dtype=np.float32`` returns that float64 result rounded to float32
-    (the reference always returns float64, which stays the default)."""
+    (the reference always returns float64, which stays the default).
+    ``mode='masked'``/``'fracb'`` imposes the branch instead of deriving it from an
+    any-NaN scan of ``field`` -- for callers that hold only part of a variable
+    (the reference decides per whole variable, remap_numpy.py:202-204)."""
     if remapper.map_filename is None and remapper._matrix is None:
         raise ValueError('No mapping file has been defined')
     _load_mapping(remapper)
     return engine.apply_weights(
         remapper._matrix, _dst_dims(remapper), field, list(remap_axes),
-        renormalization_threshold, mode='auto',
+        renormalization_threshold, mode=mode,
         device=getattr(remapper, 'device', None), return_torch=return_torch,
         out_dtype=out_dtype, out=out)

@@ -70,13 +70,15 @@ class Remapper:
     remap = remap_numpy
 
     def remap_array(self, field, remap_axes, renormalization_threshold=None,
-                    return_torch=False, out_dtype=None, out=None):
+                    return_torch=False, out_dtype=None, out=None, mode='auto'):
         """Array-level entry: numpy array or CUDA tensor in, NaN-filled float64
         out (``return_torch=True`` keeps the result on the device;
         ``out_dtype=np.float32`` rounds the float64 result to float32 on the GPU;
-        ``out=`` a preallocated host result, ideally pinned, for host inputs)."""
+        ``out=`` a preallocated host result, ideally pinned, for host inputs;
+        ``mode='masked'|'fracb'`` imposes the branch the reference would pick for the
+        whole variable when ``field`` is only a part of it)."""
         return remap_array(self, field, remap_axes, renormalization_threshold,
-                           return_torch=return_torch, out_dtype=out_dtype, out=out)
+                           return_torch=return_torch, out_dtype=out_dtype, out=out, mode=mode)
 
     # ---- out of scope (CPU, stays with pyremap) -----------------------
     def build_map(self, logger=None):
