@@ -65,15 +65,14 @@ extern "C" {
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
 /* kernel selection (0 = let the library choose: rows longer than 8 entries on average ->
- * LANES_K; masked branch with >= 2 slices per call -> WROW, in launches of at most 8 slices;
- * otherwise PBIN) */
+ * LANES_K, otherwise WROW; b200remap_auto_kernel reports the choice) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 #define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
-/* 3, 4, 5: selectors of round-1 experiments (non-persistent binned kernel, TMA / cp.async staged
- * pipelines); they lost to PBIN / WROW on B200 and were removed -- E_INVALID now */
-#define B200REMAP_KERNEL_PBIN     6  /* persistent binned CTAs, cp.async-prefetched entries    */
-#define B200REMAP_KERNEL_WROW     7  /* warp-autonomous persistent binned tiles, no CTA barrier */
+/* 3..6: selectors of experiments (non-persistent binned kernel, TMA / cp.async staged pipelines,
+ * persistent binned CTAs); they lost to WROW on B200 and were removed -- E_INVALID now */
+#define B200REMAP_KERNEL_WROW     7  /* warp tiles of the binned view, claimed dynamically in item
+                                        order by persistent warps; no CTA barrier              */
 
 typedef struct b200remap_csr b200remap_csr;
 
@@ -93,6 +92,9 @@ B200REMAP_API int b200remap_csr_create(int device, int64_t n_row, int64_t n_col,
                          const double *data, const double *frac_b,
                          int ptrs_are_device, b200remap_csr **out);
 B200REMAP_API void b200remap_csr_destroy(b200remap_csr *csr);
+
+/* the selector B200REMAP_KERNEL_AUTO resolves to for this matrix (>= 1), or a negative error */
+B200REMAP_API int b200remap_auto_kernel(const b200remap_csr *csr);
 
 /* info[0..7] = n_row, n_col, nnz, n_touched (distinct source rows referenced),
  *              max nnz per row, number of empty rows, device, has_frac_b */
@@ -183,11 +185,13 @@ B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, doubl
                            void *cuda_stream);
 
 /* tuning knobs for experiments (process-wide; 0 restores the default):
- *   0: target threads per CTA (32..384, default 160)
- *   3: cap on the vector width (1, 2, 4)               4: binning segment length in units of 32 rows
- *                                                         (read by b200remap_csr_create; default 128)
- *   2: cap on the pipeline stages of the staged kernels (2..6)   6: their shared-memory budget in KB (default 200)
- *   7: persistent CTAs per SM of the PBIN kernel (default: occupancy limit) */
+ *   0: LANES_K: target threads per CTA (32..384, default 160); WROW: 3..6 = 4..32 lanes per row
+ *   3: cap on the vector width (1, 2, 4)
+ *   4: binning segment length in units of 8 rows (read by b200remap_csr_create; default 256)
+ *   7: WROW: resident warps per SM (default: occupancy limit, 24)
+ *   8: WROW: 1 = static round-robin schedule instead of dynamic in-order claiming
+ *  12: WROW: slices per sweep of the tiles inside a launch (default 4)
+ *  14: WROW: warps per CTA (1, 2, 4; default 4)      15: WROW: shared-memory carve-out in percent */
 B200REMAP_API int b200remap_set_tunable(int which, int value);
 
 #ifdef __cplusplus

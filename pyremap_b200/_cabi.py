@@ -15,7 +15,8 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_PBIN, KERNEL_WROW = 0, 1, 2, 6, 7
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_WROW = 0, 1, 2, 7
+KERNEL_NAMES = {1: 'lanes_k_kernel', 2: 'rowblock_kernel', 7: 'wrow_kernel'}
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -26,6 +27,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
     'b200remap_spmm_f32out', 'b200remap_coo_to_csr', 'b200remap_host_pack_runs',
+    'b200remap_auto_kernel',
 )
 
 
@@ -81,6 +83,8 @@ def load_library():
         lib.b200remap_csr_destroy.argtypes = [vp]
         lib.b200remap_csr_destroy.restype = None
         lib.b200remap_csr_info.argtypes = [vp, ctypes.POINTER(i64)]
+        lib.b200remap_auto_kernel.argtypes = [vp]
+        lib.b200remap_auto_kernel.restype = i32
         lib.b200remap_spmm.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp,
                                        i64, i64, vp, i32, dbl, i32, vp]
         lib.b200remap_spmm_f32out.argtypes = lib.b200remap_spmm.argtypes
@@ -158,6 +162,13 @@ class DeviceCSR:
         (self.n_row, self.n_col, self.nnz, self.n_touched, self.max_row_nnz,
          self.n_empty_rows, self.device, has_frac) = [int(v) for v in info]
         self.has_frac_b = bool(has_frac)
+
+    def auto_kernel(self):
+        """The kernel selector ``KERNEL_AUTO`` resolves to for this matrix."""
+        code = self._lib.b200remap_auto_kernel(self._handle)
+        if code < 0:
+            check(code)
+        return code
 
     def close(self):
         if getattr(self, '_handle', None):

@@ -382,22 +382,18 @@ def _host_view(field, torch):
     return torch.from_numpy(a)
 
 
-def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch, y_f32=False,
-                         out=None):
-    """Host field in, host result out, one fused launch per leading-axis slice.
+class _Job:
+    """One variable of a streamed call: host field ``[B, nSrc, L]`` in, host result
+    ``[B, nDst, L]`` out, with its own branch (``mode_code``) and element types."""
 
-    * branch selection over the whole variable on the host (native early-exit scan),
-      because only the source rows the map touches are copied to the GPU
-      (regional maps: a few contiguous runs, :meth:`WeightMatrix.cover`);
-    * per slice: H2D on a copy stream, kernel on the current stream, D2H into pinned
-      memory on a second copy stream -- the three overlap across slices (PCIe is full
-      duplex) with double-buffered device tensors;
-    * the result: a caller-provided pinned ``out`` receives the D2H copies directly; otherwise
-      they land in a persistent pinned ring and CPU threads move each slice into a fresh
-      (pageable) array while the next slices are in flight -- page-locking a fresh result
-      block per call would cost ~0.5 ms per MB.
-    """
-    trace = _Trace()
+    def __init__(self, lay, host, mode_code, thr, y_f32, out_t):
+        self.lay, self.host, self.mode_code, self.thr = lay, host, mode_code, thr
+        self.y_f32, self.out_t = y_f32, out_t
+
+
+def _host_mode(host, threshold, mode):
+    """Branch selection over the whole variable on the host (remap_numpy.py:202-204,258-261):
+    a native early-exit scan, because only the source rows the map touches travel."""
     if mode == 'auto':
         if threshold is None:
             mode_code = MODE_FRACB
@@ -407,160 +403,229 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
         mode_code = {'raw': MODE_RAW, 'fracb': MODE_FRACB, 'masked': MODE_MASKED}[mode]
     if mode_code == MODE_MASKED and threshold is None:
         raise ValueError('the masked branch needs a renormalization threshold')
+    return mode_code
+
+
+def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, torch, y_f32=False,
+                         out=None):
+    """Host field in, host result out: a one-variable call of :func:`_stream_jobs`."""
+    mode_code = _host_mode(host, threshold, mode)
     thr = float(threshold) if threshold is not None else 0.0
-    trace.mark('host NaN scan')
+    y_dtype = torch.float32 if y_f32 else torch.float64
+    out_shape = (lay.B, lay.n_dst, lay.L)
+    out_t = torch.from_numpy(np.empty(out_shape, dtype=np.float32 if y_f32 else np.float64)) \
+        if out is None else _host_out(out, lay.out_shape, y_dtype, torch).view(out_shape)
+    job = _Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code, thr, y_f32, out_t)
+    _stream_jobs(matrix, [job], device, kernel, torch)
+    return out_t.numpy().reshape(lay.out_shape) if out is None else out
 
-    # which source rows travel: everything, a few contiguous runs (pageable memory), or -- when
-    # the field sits in pinned memory the GPU can read directly -- exactly the touched rows
-    rows_dev = None
-    dma = None
-    pack = None
-    row_bytes = lay.L * host.element_size()
-    pinned = host.is_pinned()
-    zero_copy = pinned and row_bytes % 16 == 0 and host.data_ptr() % 16 == 0
+
+def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
+                       kernel=KERNEL_AUTO):
+    """Remap several host variables through ONE streamed pipeline.
+
+    ``fields``: list of ``(array, remap_axes)``.  The reference remaps the variables of a
+    Dataset one by one (``ds.map(_remap_data_array)``, remap_numpy.py:42-55) and each pays the
+    whole chain ``.values`` -> NumPy passes -> result.  Here every variable is one *job* of a
+    single H2D / kernel / D2H pipeline: the weights are uploaded once, the side streams, pinned
+    staging rings and device buffers are shared, and the exposed first H2D / last D2H of a
+    variable overlap with its neighbours' work.  Branch selection stays per variable, exactly
+    as in the reference.  Variables the streamed path does not cover (non-contiguous, remap
+    axes not adjacent, integer dtype, ``(time, lat, lon)`` layouts) go through
+    :func:`apply_weights` one by one.  Returns the list of NaN-filled float64 results.
+    """
+    torch = _torch()
+    device = require_cuda(device)
+    results = [None] * len(fields)
+    jobs, where = [], []
+    for i, (field, remap_axes) in enumerate(fields):
+        lay = Layout(field.shape, remap_axes, dst_dims)
+        if lay.n_src != matrix.shape[1]:
+            raise ValueError(f'field has {lay.n_src} source cells but the map has '
+                             f'{matrix.shape[1]}')
+        if lay.n_dst != matrix.shape[0]:
+            raise ValueError(f'destination dims {lay.dst_dims} do not match the map '
+                             f'({matrix.shape[0]} rows)')
+        host = _host_view(field, torch) if (
+            lay.adjacent and not (lay.L == 1 and lay.B > 1) and lay.L > 0 and lay.n_dst > 0) else None
+        if host is None:
+            results[i] = apply_weights(matrix, dst_dims, field, remap_axes, threshold,
+                                       device=device, kernel=kernel)
+            continue
+        mode_code = _host_mode(host, threshold, 'auto')
+        out_t = torch.from_numpy(np.empty((lay.B, lay.n_dst, lay.L), dtype=np.float64))
+        jobs.append(_Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code,
+                         float(threshold) if threshold is not None else 0.0, False, out_t))
+        where.append(i)
+    if jobs:
+        _stream_jobs(matrix, jobs, device, kernel, torch)
+        for i, job in zip(where, jobs):
+            results[i] = job.out_t.numpy().reshape(job.lay.out_shape)
+    return results
+
+
+def _stream_jobs(matrix, jobs, device, kernel, torch):
+    """Every leading-axis slice of every job through one 3-stage pipeline, one fused launch each.
+
+    * only the source rows the map touches are copied to the GPU (regional maps: a few
+      contiguous runs, :meth:`WeightMatrix.cover_exact`);
+    * per slice: H2D on a copy stream, kernel on the current stream, D2H into pinned memory on
+      a second copy stream -- the three overlap across slices AND across variables (PCIe is
+      full duplex) with double-buffered device tensors;
+    * results: a caller-provided pinned ``out`` receives the D2H copies directly; otherwise they
+      land in a persistent pinned ring and CPU threads move each slice into the (pageable)
+      result while the next slices are in flight -- page-locking a fresh result block per call
+      would cost ~0.5 ms per MB.
+    """
+    trace = _Trace()
     cov = matrix.cover_exact()
-    if not pinned:
-        # pageable input: the copy engines cannot read it, and a plain cudaMemcpy stages it at
-        # ~10 GB/s.  CPU threads pack the touched runs (or the whole slice) into a pinned staging
-        # block (~25 GB/s) that crosses PCIe as one DMA, overlapped with the packing of the next
-        # slice (C3: 39.8 -> ~9 ms per slice).
-        if cov is not None:
-            pack = (np.ascontiguousarray(cov['run_start'] * row_bytes),
-                    np.ascontiguousarray(cov['run_pos'] * row_bytes),
-                    np.ascontiguousarray(cov['run_len'] * row_bytes))
-        else:
-            pack = (np.zeros(1, np.int64), np.zeros(1, np.int64),
-                    np.array([lay.n_src * row_bytes], np.int64))
-    elif cov is not None:
-        # pinned input, exactly the touched rows.  Few long contiguous runs: one batched DMA
-        # submission per slice (copy engines run at full rate beside the D2H of results; SM loads
-        # from host memory do not: 4.3 vs 6.3 ms per C3 slice pair).  Many short runs: the GPU
-        # gathers the rows itself.
-        import os
-        n_runs = int(cov['run_start'].size)
-        want = os.environ.get('B200REMAP_H2D', 'auto')       # 'dma' | 'gather' | 'auto' (experiments)
-        if want == 'dma' or (want == 'auto' and n_runs <= 16384
-                             and cov['n_cover'] * row_bytes >= n_runs * 32768):
-            dma = (cov['run_start'] * row_bytes, cov['run_pos'] * row_bytes,
-                   cov['run_len'] * row_bytes)
-        elif not zero_copy:
-            cov = matrix.cover()
-    if cov is None:
-        csr = matrix.on_device(device.index)
-        runs, n_x = [(0, lay.n_src, 0)], lay.n_src
-    elif pack is not None:
-        csr = matrix.on_device_cover(device.index, exact=True)
-        runs, n_x = None, cov['n_cover']
-    elif dma is not None:
-        csr = matrix.on_device_cover(device.index, exact=True)
-        runs, n_x = None, cov['n_cover']
-    elif zero_copy:
-        csr = matrix.on_device_cover(device.index, exact=True)
-        runs, n_x = None, cov['n_cover']
-        key = ('rows_dev', device.index)
-        if key not in cov:
-            cov[key] = torch.from_numpy(cov['rows']).to(device)
-        rows_dev = cov[key]
-    else:
-        csr = matrix.on_device_cover(device.index)
-        runs, n_x = cov['runs'], cov['n_cover']
-    if mode_code == MODE_FRACB and not csr.has_frac_b:
-        raise ValueError('the map has no frac_b; cannot take the unmasked branch')
+    csr = matrix.on_device(device.index) if cov is None else \
+        matrix.on_device_cover(device.index, exact=True)
+    n_x = matrix.shape[1] if cov is None else cov['n_cover']
+    n_dst = matrix.shape[0]
+    for job in jobs:
+        if job.mode_code == MODE_FRACB and not csr.has_frac_b:
+            raise ValueError('the map has no frac_b; cannot take the unmasked branch')
+    import os
+    want = os.environ.get('B200REMAP_H2D', 'auto')       # 'dma' | 'gather' | 'auto' (experiments)
+    threads = max(1, min(8, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
+                         else (os.cpu_count() or 1)))
+    total = sum(j.lay.B for j in jobs)
+    nbuf = min(2, total)
+    x_bytes = max(n_x * j.lay.L * j.host.element_size() for j in jobs)
+    y_bytes = max(n_dst * j.lay.L * j.out_t.element_size() for j in jobs)
+    rows_dev = None
 
-    B, L = lay.B, lay.L
-    src = host.view(B, lay.n_src, L)
-    code = _dtype_code(src, torch)
     with _stream_lock(device), torch.cuda.device(device):
         compute = torch.cuda.current_stream(device)
         s_in, s_out = _side_streams(device, torch)
         trace.mark('weights on device')
-        y_dtype = torch.float32 if y_f32 else torch.float64
-        nbuf = min(2, B)
-        import os
-        threads = max(1, min(8, os.cpu_count() or 1))
-        out_shape = (B, lay.n_dst, L)
-        out_t = torch.from_numpy(np.empty(out_shape, dtype=np.float32 if y_f32 else np.float64)) \
-            if out is None else _host_out(out, lay.out_shape, y_dtype, torch).view(out_shape)
-        direct = out_t.is_pinned()
-        slice_bytes = lay.n_dst * L * out_t.element_size()
-        if not direct:
-            ring_out = [r_[:slice_bytes].view(y_dtype).view(lay.n_dst, L)
-                        for r_ in _pinned_ring(torch, ('out', device.index), nbuf, slice_bytes)]
-            c_off, c_len = _chunks(slice_bytes)
+        xd = [torch.empty(x_bytes, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+        yd = [torch.empty(y_bytes, dtype=torch.uint8, device=device) for _ in range(nbuf)]
+        any_pageable = any(not j.host.is_pinned() for j in jobs)
+        any_indirect = any(not j.out_t.is_pinned() for j in jobs)
+        stage = _pinned_ring(torch, ('in', device.index), nbuf, x_bytes) if any_pageable else None
+        ring_out = _pinned_ring(torch, ('out', device.index), nbuf, y_bytes) if any_indirect else None
+        trace.mark('buffers')
         pending = [None] * nbuf     # copy-out job of the slice parked in ring_out[i]
+        stage_free = [None] * nbuf  # the DMA that last read stage[i] has finished
+        x_free = [None] * nbuf      # kernel that last read xd[i] has finished
+        y_free = [None] * nbuf      # D2H that last read yd[i] has finished
 
-        def copy_out(i, b_done, ev):      # runs on the helper thread (both calls drop the GIL)
+        def copy_out(i, dst_ptr, nbytes, ev):   # runs on the helper thread (both calls drop the GIL)
             ev.synchronize()
-            _cabi.host_pack_runs(ring_out[i].data_ptr(), out_t[b_done].data_ptr(), c_off, c_off,
-                                 c_len, threads)
+            c_off, c_len = _chunks(nbytes)
+            _cabi.host_pack_runs(ring_out[i].data_ptr(), dst_ptr, c_off, c_off, c_len, threads)
 
         def drain(i):
             if pending[i] is not None:
                 pending[i].result()
                 pending[i] = None
-        xd = [torch.empty((n_x, L), dtype=src.dtype, device=device) for _ in range(nbuf)]
-        yd = [torch.empty((lay.n_dst, L), dtype=y_dtype, device=device) for _ in range(nbuf)]
-        stage, stage_free, pack_threads = None, [None] * nbuf, threads
-        if pack is not None:
-            in_bytes = n_x * row_bytes
-            stage = [r_[:in_bytes].view(src.dtype).view(n_x, L)
-                     for r_ in _pinned_ring(torch, ('in', device.index), nbuf, in_bytes)]
-        trace.mark('buffers')
-        x_free = [None] * nbuf      # kernel that last read xd[i] has finished
-        y_free = [None] * nbuf      # D2H that last read yd[i] has finished
+
         s_in.wait_stream(compute)
-        for b in range(B):
-            i = b % nbuf
-            if pack is not None:
-                if stage_free[i] is not None:
-                    stage_free[i].synchronize()          # the DMA of slice b-2 has read stage[i]
-                _cabi.host_pack_runs(src[b].data_ptr(), stage[i].data_ptr(), pack[0], pack[1],
-                                     pack[2], pack_threads)
-            if x_free[i] is not None:
-                s_in.wait_event(x_free[i])
-            with torch.cuda.stream(s_in):
-                if pack is not None:
-                    xd[i].copy_(stage[i], non_blocking=True)
-                    stage_free[i] = torch.cuda.Event()
-                    stage_free[i].record(s_in)
-                elif dma is not None:
-                    _cabi.copy_runs(src[b].data_ptr(), xd[i].data_ptr(), dma[0], dma[1], dma[2],
-                                    s_in.cuda_stream)
-                elif rows_dev is not None:
-                    _cabi.gather_rows(src[b].data_ptr(), xd[i].data_ptr(), rows_dev.data_ptr(), n_x,
-                                      row_bytes, row_bytes, s_in.cuda_stream)
+        k = 0
+        try:
+            for job in jobs:
+                lay, src = job.lay, job.host
+                L, esz = lay.L, src.element_size()
+                row_bytes = L * esz
+                code = _dtype_code(src, torch)
+                pinned = src.is_pinned()
+                direct = job.out_t.is_pinned()
+                slice_out = n_dst * L * job.out_t.element_size()
+                # how this variable's touched rows travel
+                pack = dma = None
+                gather = False
+                if cov is None:
+                    runs = (np.zeros(1, np.int64), np.zeros(1, np.int64),
+                            np.array([lay.n_src * row_bytes], np.int64))
                 else:
-                    for start, length, pos in runs:
-                        xd[i][pos:pos + length].copy_(src[b, start:start + length],
-                                                      non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(s_in)
-            compute.wait_event(ready)
-            if y_free[i] is not None:
-                compute.wait_event(y_free[i])
-            csr.spmm(xd[i].data_ptr(), code, L, L, 1, 0, yd[i].data_ptr(), L, 0, mode_code, thr,
-                     kernel=kernel, stream=compute.cuda_stream, y_f32=y_f32)
-            done = torch.cuda.Event()
-            done.record(compute)
-            x_free[i] = done
-            s_out.wait_event(done)
-            if not direct:
-                drain(i)                 # the slice parked in ring_out[i] has reached the result
-            with torch.cuda.stream(s_out):
-                (out_t[b] if direct else ring_out[i]).copy_(yd[i], non_blocking=True)
-                fin = torch.cuda.Event()
-                fin.record(s_out)
-            y_free[i] = fin
-            if not direct:
-                pending[i] = _copy_pool().submit(copy_out, i, b, fin)
-        for t in xd + yd:            # the side streams still use these buffers
-            t.record_stream(s_in)
-            t.record_stream(s_out)
-        trace.mark('enqueue')
-        if not direct:
+                    runs = (np.ascontiguousarray(cov['run_start'] * row_bytes),
+                            np.ascontiguousarray(cov['run_pos'] * row_bytes),
+                            np.ascontiguousarray(cov['run_len'] * row_bytes))
+                if not pinned:
+                    # pageable input: the copy engines cannot read it, and a plain cudaMemcpy stages
+                    # it at ~10 GB/s.  CPU threads pack the touched runs into a pinned staging block
+                    # (~25 GB/s) that crosses PCIe as one DMA, overlapped with the next slice's packing
+                    pack = runs
+                else:
+                    # pinned input.  Few long contiguous runs: one batched DMA submission per slice
+                    # (copy engines run at full rate beside the D2H of results; SM loads from host
+                    # memory do not).  Many short runs: the GPU gathers the rows itself.
+                    n_runs = int(runs[0].size)
+                    zero_copy = cov is not None and row_bytes % 16 == 0 and src.data_ptr() % 16 == 0
+                    if want == 'gather' and zero_copy or (
+                            want == 'auto' and zero_copy and not (
+                                n_runs <= 16384 and n_x * row_bytes >= n_runs * 32768)):
+                        gather = True
+                        key = ('rows_dev', device.index)
+                        if key not in cov:
+                            cov[key] = torch.from_numpy(cov['rows']).to(device)
+                        rows_dev = cov[key]
+                    else:
+                        dma = runs
+                for b in range(lay.B):
+                    i = k % nbuf
+                    k += 1
+                    x_view = xd[i][:n_x * row_bytes]
+                    y_view = yd[i][:slice_out]
+                    if pack is not None:
+                        if stage_free[i] is not None:
+                            stage_free[i].synchronize()      # the DMA of slice k-2 has read stage[i]
+                        _cabi.host_pack_runs(src[b].data_ptr(), stage[i].data_ptr(), pack[0], pack[1],
+                                             pack[2], threads)
+                    if x_free[i] is not None:
+                        s_in.wait_event(x_free[i])
+                    with torch.cuda.stream(s_in):
+                        if pack is not None:
+                            x_view.copy_(stage[i][:n_x * row_bytes], non_blocking=True)
+                            stage_free[i] = torch.cuda.Event()
+                            stage_free[i].record(s_in)
+                        elif gather:
+                            _cabi.gather_rows(src[b].data_ptr(), x_view.data_ptr(), rows_dev.data_ptr(),
+                                              n_x, row_bytes, row_bytes, s_in.cuda_stream)
+                        else:
+                            _cabi.copy_runs(src[b].data_ptr(), x_view.data_ptr(), dma[0], dma[1],
+                                            dma[2], s_in.cuda_stream)
+                        ready = torch.cuda.Event()
+                        ready.record(s_in)
+                    compute.wait_event(ready)
+                    if y_free[i] is not None:
+                        compute.wait_event(y_free[i])
+                    csr.spmm(x_view.data_ptr(), code, L, L, 1, 0, y_view.data_ptr(), L, 0,
+                             job.mode_code, job.thr, kernel=kernel, stream=compute.cuda_stream,
+                             y_f32=job.y_f32)
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    x_free[i] = done
+                    s_out.wait_event(done)
+                    if ring_out is not None:
+                        drain(i)             # the slice parked in ring_out[i] has reached its result
+                    dst_host = job.out_t[b]
+                    with torch.cuda.stream(s_out):
+                        if direct:
+                            dst_host.view(-1).view(torch.uint8).copy_(y_view, non_blocking=True)
+                        else:
+                            ring_out[i][:slice_out].copy_(y_view, non_blocking=True)
+                        fin = torch.cuda.Event()
+                        fin.record(s_out)
+                    y_free[i] = fin
+                    if not direct:
+                        pending[i] = _copy_pool().submit(copy_out, i, dst_host.data_ptr(), slice_out, fin)
+            trace.mark('enqueue')
+        finally:
+            # whatever happened above, nothing may still read the shared pinned rings or write a
+            # result when the lock is released: drain the helper thread and the three streams
             for i in range(nbuf):
-                drain(i)
-        s_out.synchronize()
+                try:
+                    drain(i)
+                except Exception:      # noqa: BLE001 - the original exception matters more
+                    pass
+            for t in xd + yd:            # the side streams still use these buffers
+                t.record_stream(s_in)
+                t.record_stream(s_out)
+            s_in.synchronize()
+            compute.synchronize()
+            s_out.synchronize()
         trace.mark('drain')
-    trace.report(f'streamed remap B={B} L={L} rows_copied={n_x}')
-    return out_t.numpy().reshape(lay.out_shape) if out is None else out
+    trace.report(f'streamed remap: {len(jobs)} variable(s), {total} slice(s), rows_copied={n_x}')

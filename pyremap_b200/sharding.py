@@ -141,6 +141,41 @@ class ShardedRemap:
         lo, hi = self.local_slices(n_slices)
         return self._run(loader(lo, hi))
 
+    def sweep(self, loader, n_slices, chunk=8, sink=None, masked=None):
+        """Remap this rank's block ``[lo, hi)`` of an ``n_slices`` variable chunk by chunk (a
+        year of daily slices does not fit one GPU at once): ``loader(a, b)`` returns slices
+        ``[a, b)``, ``sink(a, b, out)`` consumes each result (default: results are
+        concatenated and returned).  The branch is decided once for the whole variable before
+        the first chunk is remapped: pass ``masked`` when it is known, otherwise every rank
+        scans its block through ``loader`` first and the flags are combined over the ranks."""
+        import torch
+        lo, hi = self.local_slices(n_slices)
+        spans = [(a, min(hi, a + chunk)) for a in range(lo, hi, chunk)]
+        if self._takes_branch and masked is None:
+            flag = False
+            if self.threshold is not None:
+                for a, b in spans:
+                    if block_has_nan(loader(a, b)):
+                        flag = True
+                        break
+                if self.world > 1:
+                    t = torch.tensor([1 if flag else 0], dtype=torch.int32,
+                                     device=self._flag_device())
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+                    flag = bool(int(t.item()))
+            masked = flag
+        outs = []
+        for a, b in spans:
+            block = loader(a, b)
+            out = self.compute(block, masked) if self._takes_branch else self.compute(block)
+            if sink is not None:
+                sink(a, b, out)
+            else:
+                outs.append(out)
+        if sink is not None:
+            return None
+        return torch.cat(outs, dim=0) if outs else None
+
     def gather(self, local_out, n_slices):
         """All ranks receive the full ``[T, ...]`` output (optional epilogue)."""
         import torch

@@ -41,13 +41,28 @@ def main():
     ap.add_argument('--sustain', type=int, default=1)
     ap.add_argument('--variants', default='0')
     ap.add_argument('--pfs', default='0')
+    ap.add_argument('--wpcs', default='0')
+    ap.add_argument('--carves', default='0')
+    ap.add_argument('--dump', type=int, default=0)
+    ap.add_argument('--group', type=int, default=0)
     ap.add_argument('--dyns', default='1,0')
     ap.add_argument('--kernels', default='7')
     ap.add_argument('--mode', default='masked')
     a = ap.parse_args()
-    m = syn.make_c3(order=a.order)
-    ip, ix, d = mapfile.coo_to_csr(m.S, m.row.astype(np.int64) - 1, m.col.astype(np.int64) - 1,
-                                   m.n_b, m.n_a)
+    cache = f'/tmp/c3_csr_{a.order}.npz'
+    if os.path.exists(cache):
+        z = np.load(cache)
+        ip, ix, d = z['ip'], z['ix'], z['d']
+
+        class M:
+            pass
+        m = M()
+        m.n_a, m.n_b, m.frac_b = int(z['n_a']), int(z['n_b']), z['frac_b']
+    else:
+        m = syn.make_c3(order=a.order)
+        ip, ix, d = mapfile.coo_to_csr(m.S, m.row.astype(np.int64) - 1, m.col.astype(np.int64) - 1,
+                                       m.n_b, m.n_a)
+        np.savez(cache, ip=ip, ix=ix, d=d, frac_b=m.frac_b, n_a=m.n_a, n_b=m.n_b)
     K = 80
     nbs = [int(v) for v in a.nbs.split(',')]
     ring = make_ring(m.n_a, K, max(8, max(nbs)), a.mode == 'masked')
@@ -65,18 +80,31 @@ def main():
         csr = fresh_csr(m, ip, ix, d, seg)
         for nb in nbs:
             nbytes = launch_bytes(csr, K, nb)
-            for dyn, var, kern, pf in [(int(dy), int(v), int(k), int(f)) for k in a.kernels.split(',')
-                                       for dy in a.dyns.split(',') for v in a.variants.split(',')
-                                       for f in a.pfs.split(',')]:
+            for dyn, var, kern, pf, wpc, carve in [
+                    (int(dy), int(v), int(k), int(f), int(w), int(cv)) for k in a.kernels.split(',')
+                    for dy in a.dyns.split(',') for v in a.variants.split(',')
+                    for f in a.pfs.split(',') for w in a.wpcs.split(',') for cv in a.carves.split(',')]:
                 for grid in [int(v) for v in a.grids.split(',')]:
                     _cabi.set_tunable(8, 0 if dyn else 1)
                     _cabi.set_tunable(9, var)
                     _cabi.set_tunable(13, pf)
+                    _cabi.set_tunable(14, wpc)
+                    _cabi.set_tunable(15, carve)
                     _cabi.set_tunable(7, grid)
-                    _cabi.set_tunable(12, nb)
+                    _cabi.set_tunable(12, a.group)
                     ms, best = time_launch(lambda i: run(csr, nb, i, kern), reps=12)
+                    if a.dump:
+                        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                               for _ in range(24)]
+                        for i, (e0, e1) in enumerate(evs):
+                            e0.record()
+                            run(csr, nb, i, kern)
+                            e1.record()
+                        torch.cuda.synchronize()
+                        print('   per-launch us:', ' '.join(f'{e0.elapsed_time(e1) * 1e3:.0f}' for e0, e1 in evs),
+                              flush=True)
                     gbs = nbytes / (ms * 1e-3) / 1e9
-                    line = (f'{a.mode} order={a.order} seg={seg or 512} nb={nb} kernel={kern} dyn={dyn} var={var} pf={pf} '
+                    line = (f'{a.mode} order={a.order} seg={seg or 256} group={a.group or 8} nb={nb} kernel={kern} dyn={dyn} pf={pf} wpc={wpc} carve={carve} '
                             f'warps/SM={grid or "occ"}  '
                             f'median {ms * 1e3:8.1f} us best {best * 1e3:8.1f} us  {gbs:7.1f} GB/s '
                             f'{gbs / PEAK * 100:5.1f}%')
@@ -93,7 +121,7 @@ def main():
                         g2 = nbytes / (sms * 1e-3) / 1e9
                         line += f'   sustained {sms * 1e3:8.1f} us {g2:7.1f} GB/s {g2 / PEAK * 100:5.1f}%'
                     print(line, flush=True)
-        for t in (7, 8, 9, 12, 13):
+        for t in (7, 8, 9, 12, 13, 14, 15):
             _cabi.set_tunable(t, 0)
         del csr
 

@@ -87,7 +87,7 @@ def sweep_c3(args):
         for nb in (1, 8):
             nbytes = alg_bytes(csr, K) * nb
             # (kernel, target threads, gather policy, max straight-line class)
-            variants = [(6, 160, 0, 0), (7, 0, 0, 0)]
+            variants = [(7, 0, 0, 0)]
             if args.full:
                 variants += [(1, 160, 0, 0)]
             for kern, threads, pol, maxn in variants:
@@ -133,12 +133,14 @@ def sweep_c2(args):
     ring = make_ring(m.n_a, 60, 12, True)
     y = torch.empty((12, m.n_b, 60), dtype=torch.float64, device='cuda')
     nbytes = alg_bytes(csr, 720)
-    for kern in (6, 7, 1):
+    for kern, lw in ((7, 0), (7, 3), (7, 4), (7, 5), (1, 0)):
+        _cabi.set_tunable(0, lw)
         ms, best = time_launch(lambda i: run_spmm(csr, ring, y, 60, 12, _cabi.MODE_MASKED, i, kern))
-        report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern}', ms, best, nbytes)
+        report('C2 masked (12,nCells,60)', f'batched x12 K=60 kernel={kern} lw={lw}', ms, best, nbytes)
+    _cabi.set_tunable(0, 0)
     flat = ring.permute(1, 0, 2).reshape(1, m.n_a, 720).contiguous()
     y2 = torch.empty((1, m.n_b, 720), dtype=torch.float64, device='cuda')
-    for kern, lw in ((0, 0), (6, 0), (7, 0), (7, 4), (7, 5), (7, 6), (1, 0)):
+    for kern, lw in ((0, 0), (7, 4), (7, 5), (7, 6), (1, 0)):
         _cabi.set_tunable(0, lw)         # WROW: lanes per row = 1 << (lw - 1)
         ms, best = time_launch(lambda i: run_spmm(csr, flat, y2, 720, 1, _cabi.MODE_MASKED, i, kern))
         report('C2 masked [nCells,720]', f'flat K=720 kernel={kern} lw={lw}', ms, best, nbytes)
@@ -150,7 +152,7 @@ def sweep_c1(args):
     csr = device_csr(m)
     x = torch.randn((1, m.n_a, 10), dtype=torch.float64, device='cuda')
     y = torch.empty((1, m.n_b, 10), dtype=torch.float64, device='cuda')
-    for kern in (6, 7, 1):
+    for kern in (7, 1):
         ms, best = time_launch(lambda i: run_spmm(csr, x, y, 10, 1, _cabi.MODE_FRACB, i, kern), reps=50)
         report('C1 unmasked K=10', f'kernel={kern} (latency)', ms, best, alg_bytes(csr, 10))
 
@@ -163,7 +165,7 @@ def sweep_c4(args):
         x = make_ring(m.n_a, K, 2, False)
         x[:, :: 97, :] = float('nan')
         y = torch.empty((1, m.n_b, K), dtype=torch.float64, device='cuda')
-        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (6, 'pbin'), (7, 'wrow')):
+        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (7, 'wrow')):
             ms, best = time_launch(lambda i: run_spmm(csr, x, y, K, 1, _cabi.MODE_MASKED, i, kernel))
             report(f'C4 masked K={K}', name, ms, best, alg_bytes(csr, K))
 
