@@ -299,9 +299,10 @@ def csr_of(m, device_index):
     return matrix, csr, info
 
 
-def kernel_name(csr, dtype='double', vec=4, mode=2):
+def kernel_name(csr, dtype='double', vec=4, mode=2, K=N_LEVELS):
     from pyremap_b200 import _cabi
-    return f'{_cabi.KERNEL_NAMES.get(csr.auto_kernel(), "?")}<{dtype},VEC={vec},MODE={mode}>'
+    code = _cabi.F64 if dtype == 'double' else _cabi.F32
+    return f'{_cabi.KERNEL_NAMES.get(csr.auto_kernel(code, K), "?")}<{dtype},VEC={vec},MODE={mode}>'
 
 
 def time_launches(torch, fn, reps=20, warm=3, flush=None):
@@ -619,18 +620,36 @@ def measure_dropin(args, torch, dist, m, matrix, device, world, ring):
          'xtime': (('Time', 'StrLen'), np.zeros((T, 4), dtype='S1'))},
         coords={'Time': np.arange(T, dtype=np.float64)})
     thr = THRESHOLD if args.mode == 'masked' else None
-    out = r.remap_numpy(ds, thr)                     # warm-up
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(device)
-    t0 = time.perf_counter()
-    out = r.remap_numpy(ds, thr)
-    torch.cuda.synchronize(device)
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
+    from pyremap_b200 import engine
+
+    def timed_call():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        res = r.remap_numpy(ds, thr)
+        torch.cuda.synchronize(device)
+        dt_ = time.perf_counter() - t0
+        tt = torch.tensor([dt_], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return res, float(tt.item())
+
+    # steady state of a loop `out = remapper.remap_numpy(ds_t, thr)`: the previous result has been
+    # dropped, its buffers were page-locked by the pool's helper thread and are written directly
+    out = None
+    for _ in range(2):                               # warm-up: streams, staging rings, result pool
+        out = None
+        engine._RESULTS.wait_idle()
+        out, _ = timed_call()
+    out = None
+    engine._RESULTS.wait_idle()
+    out, dt = timed_call()
+    # the same call while the caller still holds the previous result (no buffer to recycle:
+    # pageable result filled through the pinned ring by CPU threads)
+    keep = out
+    out, dt_retained = timed_call()
+    del keep
     n = 2 * T
     assert out['temperature'].values.shape == (T,) + tuple(m.dst_descriptor.dim_sizes) + (N_LEVELS,)
     cov = matrix.cover_exact()
@@ -642,7 +661,8 @@ def measure_dropin(args, torch, dist, m, matrix, device, world, ring):
                    f'nVertLevels={N_LEVELS}) float64, xtime}}, {thr}): pageable arrays in, fresh '
                    'float64 arrays out; host NaN scan per variable, CPU threads pack the touched runs '
                    'into pinned staging, one pipeline for all variables',
-           'container': flavour, 'variables': 2, 'slices_per_call': n}
+           'container': flavour, 'variables': 2, 'slices_per_call': n,
+           'ms_per_slice_previous_result_still_held': dt_retained / n * 1e3}
     del ds, out, a, b
     return res
 
@@ -699,7 +719,7 @@ def measure_configs(args, torch, device, m3, csr3, info3, ring, peak):
     ms, best = time_launches(torch, lambda i: spmm(csr1, x1, y1, 10, 1, 1, m1.n_a, m1.n_b), reps=50,
                              flush=flush)
     entry('C1 2deg->1deg bilinear, K=10, frac_b branch', ms, best,
-          launch_bytes(info1, 10, 1, with_fracb=True), kernel_name(csr1, vec=2, mode=1),
+          launch_bytes(info1, 10, 1, with_fracb=True), kernel_name(csr1, vec=2, mode=1, K=10),
           latency_us=ms * 1e3, note='launch-latency bound (10 MB of traffic): the latency is the figure',
           l2='flushed between iterations')
     del csr1, x1, y1
@@ -714,14 +734,14 @@ def measure_configs(args, torch, device, m3, csr3, info3, ring, peak):
     ms, best = time_launches(torch, lambda i: spmm(csr2, nat, y2, 60, 12, 2, m2.n_a, m2.n_b),
                              flush=flush)
     entry('C2 native (Time=12, nCells, nVertLevels=60) masked', ms, best,
-          launch_bytes(info2, 60, 12), kernel_name(csr2, mode=2), slices_per_launch=12,
+          launch_bytes(info2, 60, 12), kernel_name(csr2, mode=2, K=60), slices_per_launch=12,
           l2='flushed between iterations')
     flat = nat.permute(1, 0, 2).reshape(1, m2.n_a, 720).contiguous()
     y2f = y2.view(1, m2.n_b, 720)
     ms, best = time_launches(torch, lambda i: spmm(csr2, flat, y2f, 720, 1, 2, m2.n_a, m2.n_b),
                              flush=flush)
     entry('C2 flat [nCells, K=720] masked', ms, best, launch_bytes(info2, 720, 1),
-          kernel_name(csr2, mode=2), slices_per_launch=1, l2='flushed between iterations')
+          kernel_name(csr2, mode=2, K=720), slices_per_launch=1, l2='flushed between iterations')
     del csr2, nat, flat, y2, y2f
 
     # ---- C4: 1 km -> 10 km stereographic, 121 entries per row, K = 1 and K = 4
@@ -734,7 +754,7 @@ def measure_configs(args, torch, device, m3, csr3, info3, ring, peak):
         ms, best = time_launches(torch, lambda i: spmm(csr4, x4[i % 2], y4, K4, 1, 2, m4.n_a, m4.n_b),
                                  flush=flush)
         entry(f'C4 1km->10km conservative (121 entries/row), K={K4}, masked', ms, best,
-              launch_bytes(info4, K4, 1), kernel_name(csr4, vec=4 if K4 == 4 else 1, mode=2),
+              launch_bytes(info4, K4, 1), kernel_name(csr4, vec=4 if K4 == 4 else 1, mode=2, K=K4),
               slices_per_launch=1, l2='flushed between iterations')
         del x4, y4
     del csr4, flush

@@ -64,13 +64,13 @@ extern "C" {
                                     Y = den > threshold ? num/den : NaN
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
-/* kernel selection (0 = let the library choose: rows longer than 8 entries on average ->
- * LANES_K, otherwise WROW; b200remap_auto_kernel reports the choice) */
+/* kernel selection (0 = let the library choose: rows of at most 8 entries on average -> WROW,
+ * longer rows -> LANES_K; b200remap_auto_kernel reports the choice) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
-#define B200REMAP_KERNEL_ROWBLOCK 2  /* small K: products staged in smem, ordered row sums    */
-/* 3..6: selectors of experiments (non-persistent binned kernel, TMA / cp.async staged pipelines,
- * persistent binned CTAs); they lost to WROW on B200 and were removed -- E_INVALID now */
+/* 2..6: selectors of experiments (shared-memory staged kernels for long rows, a non-persistent
+ * binned kernel, TMA / cp.async staged pipelines, persistent binned CTAs); they lost to
+ * LANES_K / WROW on B200 and were removed -- E_INVALID now */
 #define B200REMAP_KERNEL_WROW     7  /* warp tiles of the binned view, claimed dynamically in item
                                         order by persistent warps; no CTA barrier              */
 
@@ -94,7 +94,7 @@ B200REMAP_API int b200remap_csr_create(int device, int64_t n_row, int64_t n_col,
 B200REMAP_API void b200remap_csr_destroy(b200remap_csr *csr);
 
 /* the selector B200REMAP_KERNEL_AUTO resolves to for this matrix (>= 1), or a negative error */
-B200REMAP_API int b200remap_auto_kernel(const b200remap_csr *csr);
+B200REMAP_API int b200remap_auto_kernel(const b200remap_csr *csr, int x_dtype, int64_t K);
 
 /* info[0..7] = n_row, n_col, nnz, n_touched (distinct source rows referenced),
  *              max nnz per row, number of empty rows, device, has_frac_b */
@@ -116,8 +116,7 @@ B200REMAP_API int b200remap_spmm(const b200remap_csr *csr, const void *X, int x_
 /* The same product with a float32 result: every element is the float64 value b200remap_spmm
  * writes, rounded to nearest float32 (so it equals numpy's `.astype(float32)` of the reference's
  * result bit for bit; NaN placement unchanged).  Halves the output traffic for float32 workflows
- * (SURVEY §8f rank 3).  Y strides are in float32 elements.  Not offered by the ROWBLOCK / TMA /
- * STAGED kernel selectors. */
+ * (SURVEY §8f rank 3).  Y strides are in float32 elements. */
 B200REMAP_API int b200remap_spmm_f32out(const b200remap_csr *csr, const void *X, int x_dtype,
                    int64_t K, int64_t ldx, int64_t nbatch, int64_t x_batch_stride,
                    const uint8_t *valid, float *Y, int64_t ldy, int64_t y_batch_stride,

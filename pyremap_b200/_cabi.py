@@ -15,8 +15,8 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-KERNEL_AUTO, KERNEL_LANES_K, KERNEL_ROWBLOCK, KERNEL_WROW = 0, 1, 2, 7
-KERNEL_NAMES = {1: 'lanes_k_kernel', 2: 'rowblock_kernel', 7: 'wrow_kernel'}
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_WROW = 0, 1, 7
+KERNEL_NAMES = {1: 'lanes_k_kernel', 7: 'wrow_kernel'}
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares
@@ -83,7 +83,7 @@ def load_library():
         lib.b200remap_csr_destroy.argtypes = [vp]
         lib.b200remap_csr_destroy.restype = None
         lib.b200remap_csr_info.argtypes = [vp, ctypes.POINTER(i64)]
-        lib.b200remap_auto_kernel.argtypes = [vp]
+        lib.b200remap_auto_kernel.argtypes = [vp, i32, i64]
         lib.b200remap_auto_kernel.restype = i32
         lib.b200remap_spmm.argtypes = [vp, vp, i32, i64, i64, i64, i64, vp, vp,
                                        i64, i64, vp, i32, dbl, i32, vp]
@@ -163,9 +163,9 @@ class DeviceCSR:
          self.n_empty_rows, self.device, has_frac) = [int(v) for v in info]
         self.has_frac_b = bool(has_frac)
 
-    def auto_kernel(self):
-        """The kernel selector ``KERNEL_AUTO`` resolves to for this matrix."""
-        code = self._lib.b200remap_auto_kernel(self._handle)
+    def auto_kernel(self, x_dtype=F64, K=80):
+        """The kernel selector ``KERNEL_AUTO`` resolves to for this matrix and field row."""
+        code = self._lib.b200remap_auto_kernel(self._handle, int(x_dtype), int(K))
         if code < 0:
             check(code)
         return code

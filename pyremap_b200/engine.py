@@ -340,6 +340,115 @@ def _pinned_ring(torch, tag, count, nbytes):
     return ring
 
 
+class _Buf:
+    """One recycled result buffer: a CPU uint8 tensor, page-locked once it has been released."""
+
+    def __init__(self, tensor):
+        self.tensor, self.pinned = tensor, False
+
+
+class _ResultPool:
+    """Recycled result buffers of the streamed path.
+
+    A fresh pageable result costs a CPU copy out of the pinned D2H ring plus the first-touch
+    page faults of the new array (C3: ~8 ms per 193 MB slice); page-locking a fresh block inside
+    a call would cost ~0.5 ms per MB.  So results are numpy arrays backed by buffers of this
+    pool.  The first result of a size is ordinary pageable memory (filled through the ring, as
+    before).  When the caller drops it -- the array and every view of it -- a helper thread
+    page-locks the buffer (``cudaHostRegister``) and parks it; the next result of that size is
+    then written by the device->host copies directly, with no CPU copy and no page faults.
+    Callers that keep every result alive simply stay on the pageable path.  The pool holds at
+    most ``B200REMAP_RESULT_POOL_GB`` (default 8) of buffers; beyond that results are plain arrays.
+    """
+
+    def __init__(self):
+        import os
+        import threading
+        self.free = []
+        self.bytes = 0
+        self.lock = threading.Lock()
+        self.budget = int(float(os.environ.get('B200REMAP_RESULT_POOL_GB', '8')) * (1 << 30))
+        self.worker = None
+
+    def take(self, nbytes):
+        """A parked page-locked buffer that fits ``nbytes`` without wasting half of it."""
+        with self.lock:
+            best = None
+            for i, buf in enumerate(self.free):
+                n = buf.tensor.numel()
+                if buf.pinned and nbytes <= n <= 2 * nbytes and (best is None or n < self.free[best].tensor.numel()):
+                    best = i
+            return self.free.pop(best) if best is not None else None
+
+    def fresh(self, nbytes, torch):
+        """A new pageable buffer the pool will recycle, or None when the budget is used up."""
+        with self.lock:
+            while self.bytes + nbytes > self.budget and self.free:
+                self._drop(self.free.pop(0), torch)
+            if self.bytes + nbytes > self.budget:
+                return None
+            self.bytes += nbytes
+        return _Buf(torch.empty(max(int(nbytes), 1), dtype=torch.uint8))
+
+    def _drop(self, buf, torch):
+        if buf.pinned:
+            torch.cuda.cudart().cudaHostUnregister(buf.tensor.data_ptr())
+        self.bytes -= buf.tensor.numel()
+
+    def release(self, buf, device_index):
+        """Finalizer of a handed-out array: page-lock (once) and park the buffer, off-thread."""
+        try:
+            if self.worker is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self.worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix='b200remap-pin')
+            self.worker.submit(self._park, buf, device_index)
+        except RuntimeError:            # interpreter shutting down
+            pass
+
+    def _park(self, buf, device_index):
+        torch = _torch()
+        if not buf.pinned:
+            try:
+                torch.cuda.set_device(device_index)
+                err = torch.cuda.cudart().cudaHostRegister(buf.tensor.data_ptr(),
+                                                           buf.tensor.numel(), 1)   # portable
+                buf.pinned = int(err) == 0
+            except Exception:           # noqa: BLE001 - stay pageable, but do not keep it
+                buf.pinned = False
+        with self.lock:
+            if buf.pinned:
+                self.free.append(buf)
+            else:
+                self.bytes -= buf.tensor.numel()
+
+    def wait_idle(self):
+        """Block until every released buffer has been parked (tests, benchmarks)."""
+        if self.worker is not None:
+            self.worker.submit(lambda: None).result()
+
+
+_RESULTS = _ResultPool()
+
+
+def _new_result(shape, np_dtype, torch, device_index):
+    """(host tensor of ``shape``, numpy array to return, direct) -- ``direct``: the tensor is
+    page-locked, device->host copies may target it."""
+    import weakref
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(np_dtype).itemsize
+    buf = None
+    if nbytes >= (1 << 20):
+        buf = _RESULTS.take(nbytes) or _RESULTS.fresh(nbytes, torch)
+    if buf is None:
+        arr = np.empty(shape, dtype=np_dtype)
+        return torch.from_numpy(arr), arr, False
+    t_dtype = torch.float32 if np.dtype(np_dtype) == np.float32 else torch.float64
+    t = buf.tensor[:nbytes].view(t_dtype).view(shape)
+    arr = t.numpy()              # its base is the tensor, so every view of arr keeps arr alive
+    fin = weakref.finalize(arr, _RESULTS.release, buf, device_index)
+    fin.atexit = False
+    return t, arr, buf.pinned
+
+
 _POOL = []
 
 
@@ -386,9 +495,11 @@ class _Job:
     """One variable of a streamed call: host field ``[B, nSrc, L]`` in, host result
     ``[B, nDst, L]`` out, with its own branch (``mode_code``) and element types."""
 
-    def __init__(self, lay, host, mode_code, thr, y_f32, out_t):
+    def __init__(self, lay, host, mode_code, thr, y_f32, out_t, direct=None):
         self.lay, self.host, self.mode_code, self.thr = lay, host, mode_code, thr
         self.y_f32, self.out_t = y_f32, out_t
+        # direct: device->host copies may land in out_t itself (page-locked memory)
+        self.direct = out_t.is_pinned() if direct is None else direct
 
 
 def _host_mode(host, threshold, mode):
@@ -413,11 +524,15 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     thr = float(threshold) if threshold is not None else 0.0
     y_dtype = torch.float32 if y_f32 else torch.float64
     out_shape = (lay.B, lay.n_dst, lay.L)
-    out_t = torch.from_numpy(np.empty(out_shape, dtype=np.float32 if y_f32 else np.float64)) \
-        if out is None else _host_out(out, lay.out_shape, y_dtype, torch).view(out_shape)
-    job = _Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code, thr, y_f32, out_t)
+    arr, direct = None, None
+    if out is None:
+        out_t, arr, direct = _new_result(out_shape, np.float32 if y_f32 else np.float64, torch,
+                                         device.index)
+    else:
+        out_t = _host_out(out, lay.out_shape, y_dtype, torch).view(out_shape)
+    job = _Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code, thr, y_f32, out_t, direct)
     _stream_jobs(matrix, [job], device, kernel, torch)
-    return out_t.numpy().reshape(lay.out_shape) if out is None else out
+    return arr.reshape(lay.out_shape) if out is None else out
 
 
 def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
@@ -453,14 +568,14 @@ def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
                                        device=device, kernel=kernel)
             continue
         mode_code = _host_mode(host, threshold, 'auto')
-        out_t = torch.from_numpy(np.empty((lay.B, lay.n_dst, lay.L), dtype=np.float64))
+        out_t, arr, direct = _new_result((lay.B, lay.n_dst, lay.L), np.float64, torch, device.index)
         jobs.append(_Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code,
-                         float(threshold) if threshold is not None else 0.0, False, out_t))
-        where.append(i)
+                         float(threshold) if threshold is not None else 0.0, False, out_t, direct))
+        where.append((i, arr))
     if jobs:
         _stream_jobs(matrix, jobs, device, kernel, torch)
-        for i, job in zip(where, jobs):
-            results[i] = job.out_t.numpy().reshape(job.lay.out_shape)
+        for (i, arr), job in zip(where, jobs):
+            results[i] = arr.reshape(job.lay.out_shape)
     return results
 
 
@@ -488,7 +603,7 @@ def _stream_jobs(matrix, jobs, device, kernel, torch):
             raise ValueError('the map has no frac_b; cannot take the unmasked branch')
     import os
     want = os.environ.get('B200REMAP_H2D', 'auto')       # 'dma' | 'gather' | 'auto' (experiments)
-    threads = max(1, min(8, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
+    threads = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
                          else (os.cpu_count() or 1)))
     total = sum(j.lay.B for j in jobs)
     nbuf = min(2, total)
@@ -503,7 +618,7 @@ def _stream_jobs(matrix, jobs, device, kernel, torch):
         xd = [torch.empty(x_bytes, dtype=torch.uint8, device=device) for _ in range(nbuf)]
         yd = [torch.empty(y_bytes, dtype=torch.uint8, device=device) for _ in range(nbuf)]
         any_pageable = any(not j.host.is_pinned() for j in jobs)
-        any_indirect = any(not j.out_t.is_pinned() for j in jobs)
+        any_indirect = any(not j.direct for j in jobs)
         stage = _pinned_ring(torch, ('in', device.index), nbuf, x_bytes) if any_pageable else None
         ring_out = _pinned_ring(torch, ('out', device.index), nbuf, y_bytes) if any_indirect else None
         trace.mark('buffers')
@@ -531,7 +646,7 @@ def _stream_jobs(matrix, jobs, device, kernel, torch):
                 row_bytes = L * esz
                 code = _dtype_code(src, torch)
                 pinned = src.is_pinned()
-                direct = job.out_t.is_pinned()
+                direct = job.direct
                 slice_out = n_dst * L * job.out_t.element_size()
                 # how this variable's touched rows travel
                 pack = dma = None

@@ -165,9 +165,13 @@ def sweep_c4(args):
         x = make_ring(m.n_a, K, 2, False)
         x[:, :: 97, :] = float('nan')
         y = torch.empty((1, m.n_b, K), dtype=torch.float64, device='cuda')
-        for kernel, name in ((2, 'rowblock'), (1, 'lanes_k'), (7, 'wrow')):
-            ms, best = time_launch(lambda i: run_spmm(csr, x, y, K, 1, _cabi.MODE_MASKED, i, kernel))
-            report(f'C4 masked K={K}', name, ms, best, alg_bytes(csr, K))
+        for kernel, name, ts in ((1, 'lanes_k', 0),):
+            _cabi.set_tunable(5, ts)
+            for mode, mname in ((_cabi.MODE_MASKED, 'masked'), (_cabi.MODE_FRACB, 'fracb')):
+                xin = x if mode == _cabi.MODE_MASKED else torch.nan_to_num(x, nan=1.0)
+                ms, best = time_launch(lambda i: run_spmm(csr, xin, y, K, 1, mode, i, kernel))
+                report(f'C4 {mname} K={K}', name, ms, best, alg_bytes(csr, K))
+        _cabi.set_tunable(5, 0)
 
 
 if __name__ == '__main__':
