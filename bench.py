@@ -64,6 +64,8 @@ def parse_args():
     ap.add_argument('--no-sharded', action='store_true')
     ap.add_argument('--e2e-slices', type=int, default=8, help='slices per e2e call')
     ap.add_argument('--cpu-seconds', type=float, default=20.0)
+    ap.add_argument('--order', default='rings', choices=['rings', 'blocks', 'shuffle'],
+                    help='numbering of the synthetic source cells (mesh-order sensitivity runs)')
     return ap.parse_args()
 
 
@@ -84,7 +86,8 @@ def bench_config(args):
             'branch': args.mode, 'threshold': THRESHOLD if args.mode == 'masked' else None,
             'gpu_batching': f'(Time={BATCH}, nCells, nVertLevels) per fused launch over a ring of '
                             f'{RING} distinct slices resident in HBM (larger than L2: no flush needed)',
-            'parallelism': 'weights replicated, slices sharded over the ranks, no collective'}
+            'parallelism': 'weights replicated, slices sharded over the ranks, no collective',
+            'source_cell_order': args.order}
 
 
 def weight_bytes(info, with_fracb):
@@ -345,7 +348,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
 
-    m = syn.make_c3(scale=args.scale)
+    m = syn.make_c3(scale=args.scale, order=args.order)
     matrix, csr, info = csr_of(m, local)
     masked = args.mode == 'masked'
     mode_code = _cabi.MODE_MASKED if masked else _cabi.MODE_FRACB
@@ -449,7 +452,7 @@ def run_b200(args):
     if not args.no_e2e:
         out['e2e'] = measure_e2e(args, torch, dist, m, matrix, device, world, ring)
         out['e2e_dropin'] = measure_dropin(args, torch, dist, m, matrix, device, world, ring)
-    if world == 1 and not args.no_configs and args.scale == 1.0:
+    if world == 1 and not args.no_configs and args.scale == 1.0 and args.order == 'rings':
         del y
         out['configs'] = measure_configs(args, torch, device, m, csr, info, ring, peak)
     if rank == 0:

@@ -182,6 +182,11 @@ B200REMAP_API int b200remap_coo_to_csr(int device, int64_t n_row, int64_t n_col,
  * division, which must equal IEEE-754 division bit for bit (pinned by the test-suite) */
 B200REMAP_API int b200remap_debug_divide(const double *a, const double *b, double *q, int64_t n,
                            void *cuda_stream);
+/* the same through the branch-free division of the masked epilogue (what MODE_MASKED runs for
+ * num / den); every denominator is treated as kept, so q[i] must equal a[i] / b[i] for finite
+ * positive b[i] */
+B200REMAP_API int b200remap_debug_divide_masked(const double *a, const double *b, double *q,
+                                  int64_t n, void *cuda_stream);
 
 /* tuning knobs for experiments (process-wide; 0 restores the default):
  *   0: LANES_K: target threads per CTA (32..384, default 160); WROW: 3..6 = 4..32 lanes per row

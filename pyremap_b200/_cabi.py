@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
     'b200remap_spmm_f32out', 'b200remap_coo_to_csr', 'b200remap_host_pack_runs',
-    'b200remap_auto_kernel',
+    'b200remap_auto_kernel', 'b200remap_debug_divide_masked',
 )
 
 
@@ -64,6 +64,11 @@ def load_library():
                     raise B200RemapError(
                         -3, f'{path} is missing and could not be built ({exc}); '
                         'pyremap_b200 has no CPU fallback') from exc
+                import warnings
+                warnings.warn(
+                    f'{path} is older than its sources and could not be rebuilt ({exc}); '
+                    'loading the stale library -- kernel fixes in the sources are NOT in effect',
+                    RuntimeWarning, stacklevel=2)
         try:
             lib = ctypes.CDLL(path)
         except OSError as exc:
@@ -95,6 +100,8 @@ def load_library():
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
         lib.b200remap_set_tunable.argtypes = [i32, i32]
         lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
+        lib.b200remap_debug_divide_masked.argtypes = [vp, vp, vp, i64, vp]
+        lib.b200remap_debug_divide_masked.restype = i32
         lib.b200remap_host_any_nan.argtypes = [vp, i32, i64, i32, ctypes.POINTER(i32)]
         lib.b200remap_gather_rows.argtypes = [vp, vp, vp, i64, i64, i64, vp]
         lib.b200remap_copy_runs.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
@@ -212,8 +219,10 @@ def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0):
         ctypes.c_void_p(stream) if stream else None))
 
 
-def debug_divide(a_ptr, b_ptr, q_ptr, n, stream=0):
-    check(load_library().b200remap_debug_divide(
+def debug_divide(a_ptr, b_ptr, q_ptr, n, stream=0, masked=False):
+    lib = load_library()
+    fn = lib.b200remap_debug_divide_masked if masked else lib.b200remap_debug_divide
+    check(fn(
         ctypes.c_void_p(a_ptr), ctypes.c_void_p(b_ptr), ctypes.c_void_p(q_ptr), int(n),
         ctypes.c_void_p(stream) if stream else None))
 

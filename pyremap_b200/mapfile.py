@@ -156,7 +156,7 @@ def coo_to_csr(S, row0, col0, n_row, n_col):
     return indptr, indices, np.ascontiguousarray(S, dtype=np.float64)
 
 
-def coo_to_csr_gpu(S, row0, col0, n_row, n_col, device=0):
+def coo_to_csr_gpu(S, row0, col0, n_row, n_col, device=None):
     """:func:`coo_to_csr` on the GPU (``b200remap_coo_to_csr``): counting pass, scan, one warp
     per row ranking its entries by (col, file position), duplicate runs summed in file order.
     Bit-identical to :func:`coo_to_csr`; ~50x faster for maps with tens of millions of weights."""
@@ -164,14 +164,25 @@ def coo_to_csr_gpu(S, row0, col0, n_row, n_col, device=0):
 
     from . import _cabi
     S = np.ascontiguousarray(S, dtype=np.float64).ravel()
-    row32 = np.ascontiguousarray(np.asarray(row0).ravel(), dtype=np.int32)
-    col32 = np.ascontiguousarray(np.asarray(col0).ravel(), dtype=np.int32)
-    if not (S.size == row32.size == col32.size):
+    row0 = np.asarray(row0).ravel()
+    col0 = np.asarray(col0).ravel()
+    if not (S.size == row0.size == col0.size):
         raise ValueError('S, row and col must have the same length')
     n_row, n_col = int(n_row), int(n_col)
     if S.size >= 2**31 - 1 or n_row >= 2**31 - 1 or n_col >= 2**31 - 1:
         raise ValueError('int32 CSR only: sizes must be below 2**31')
-    dev = torch.device('cuda', int(device))
+    # range checks on the ORIGINAL integers: an int64 index of a corrupt map must not wrap
+    # into the valid range when it is narrowed to the int32 the device builder takes
+    if S.size:
+        if row0.min() < 0 or row0.max() >= n_row:
+            raise ValueError('row index out of range for n_b')
+        if col0.min() < 0 or col0.max() >= n_col:
+            raise ValueError('col index out of range for n_a')
+    row32 = np.ascontiguousarray(row0, dtype=np.int32)
+    col32 = np.ascontiguousarray(col0, dtype=np.int32)
+    # the current device unless told otherwise (one process per GPU: never touch device 0
+    # from every rank)
+    dev = torch.device('cuda', torch.cuda.current_device() if device is None else int(device))
     with torch.cuda.device(dev):
         indptr = torch.empty(n_row + 1, dtype=torch.int32, device=dev)
         indices = torch.empty(max(S.size, 1), dtype=torch.int32, device=dev)

@@ -168,7 +168,7 @@ def _load_mapping(remapper):
     # machines that only inspect a map (no device) use the NumPy builder
     if np.size(s) >= _GPU_CSR_MIN_WEIGHTS and _cuda_ready():
         indptr, indices, data = coo_to_csr_gpu(s, row, col, n_b, n_a,
-                                               getattr(remapper, 'device', None) or 0)
+                                               getattr(remapper, 'device', None))
     else:
         indptr, indices, data = coo_to_csr(s, row, col, n_b, n_a)
     frac_b = np.asarray(ds_map['frac_b'].values, dtype=np.float64)

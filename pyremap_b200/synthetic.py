@@ -287,7 +287,9 @@ def _antarctic_stereo_xy(lat_deg, lon_deg, lat_ts=-71.0):
 def make_c3(scale=1.0, seed=3, order='rings'):
     """MPAS-like variable-resolution ocean mesh (3 693 225 cells at scale 1) ->
     Antarctic stereographic grid, 6000 x 5000 km at 10 km (601 x 501); 3..10
-    entries per ocean row, rows over the continent empty (``frac_b = 0``)."""
+    entries per ocean row, rows over the continent empty (``frac_b = 0``).
+    ``order``: numbering of the source cells -- 'rings' (latitude rings from the south pole),
+    'blocks' (compact blocks in random order, graph-partition-like) or 'shuffle' (random)."""
     from scipy.spatial import cKDTree
     rng = np.random.default_rng(seed)
     n_a = max(2000, int(round(3693225 * scale)))
@@ -295,6 +297,15 @@ def make_c3(scale=1.0, seed=3, order='rings'):
     lat_a, lon_a = _variable_resolution_rings(n_a, 6.0 * lin, 18.0 * lin)
     if order == 'shuffle':
         p = rng.permutation(n_a)
+        lat_a, lon_a = lat_a[p], lon_a[p]
+    elif order == 'blocks':
+        # graph-partition-like numbering (how MPAS meshes come out of METIS-style tools): cells
+        # of one compact block are contiguous, the blocks themselves in no geographic order
+        nb_lat, nb_lon = 48, 96
+        bi = np.minimum(((lat_a + 90.0) / 180.0 * nb_lat).astype(np.int64), nb_lat - 1)
+        bj = np.minimum(((lon_a + 180.0) / 360.0 * nb_lon).astype(np.int64), nb_lon - 1)
+        block_rank = rng.permutation(nb_lat * nb_lon)[bi * nb_lon + bj]
+        p = np.argsort(block_rank, kind='stable')
         lat_a, lon_a = lat_a[p], lon_a[p]
     dx = 10.0 * lin
     nx = int(6000.0 / dx) + 1
