@@ -524,8 +524,11 @@ def measure_sharded(args, torch, dist, m, matrix, device, world, ring):
            'value': n_total / (ms * 1e-3), 'unit': UNIT,
            'api': 'pyremap_b200.sharding.ShardedRemap.sweep -> Remapper.remap_array(CUDA tensor)',
            'slices_this_rank': hi - lo}
-    # one batch, sharded vs unsharded, bit for bit; and the optional gather
+    # one batch, sharded vs unsharded, bit for bit; and the optional gather.  Every rank holds
+    # its own synthetic ring, so rank 0's batch is broadcast first (NCCL over NVLink)
     T = min(BATCH, RING)
+    if world > 1:
+        dist.broadcast(ring[:T], src=0)
     local = sh.remap_local(ring[:T])
     torch.cuda.synchronize(device)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

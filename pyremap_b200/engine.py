@@ -603,8 +603,11 @@ def _stream_jobs(matrix, jobs, device, kernel, torch):
             raise ValueError('the map has no frac_b; cannot take the unmasked branch')
     import os
     want = os.environ.get('B200REMAP_H2D', 'auto')       # 'dma' | 'gather' | 'auto' (experiments)
-    threads = max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
-                         else (os.cpu_count() or 1)))
+    # CPU threads for packing / copying out: the cores this process may use, shared fairly with
+    # the other ranks of the node (torchrun exports LOCAL_WORLD_SIZE)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    ranks_here = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    threads = max(1, min(16, cores // ranks_here))
     total = sum(j.lay.B for j in jobs)
     nbuf = min(2, total)
     x_bytes = max(n_x * j.lay.L * j.host.element_size() for j in jobs)
