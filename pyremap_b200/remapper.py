@@ -86,6 +86,15 @@ class Remapper:
             'mapping-file generation (ESMF_RegridWeightGen / mbtempest) stays '
             'on the CPU with pyremap; pyremap_b200 only applies existing maps')
 
-    def ncremap(self, *args, **kwargs):
-        raise NotImplementedError(
-            'the NCO file-to-file path stays with pyremap; use remap_numpy')
+    def remap_file(self, in_filename, out_filename, variable_list=None, overwrite=False,
+                   renormalize=None, logger=None, replace_mpas_fill=False, parallel_exec=None):
+        """File-to-file remap on the GPU with the arguments of the reference's
+        ``Remapper.ncremap`` (remapper.py:434-506); see :mod:`pyremap_b200.remap_file`."""
+        from .remap_file import remap_file
+        return remap_file(self, in_filename, out_filename, variable_list=variable_list,
+                          overwrite=overwrite, renormalize=renormalize, logger=logger,
+                          replace_mpas_fill=replace_mpas_fill, parallel_exec=parallel_exec)
+
+    #: the reference's name of the file-to-file call; here it runs on the GPU instead of
+    #: launching NCO (same arguments, ``parallel_exec`` ignored)
+    ncremap = remap_file

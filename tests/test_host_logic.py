@@ -133,9 +133,8 @@ def test_remapper_errors_before_any_arithmetic(tmp_path):
                                dst_descriptor=wrong_dst)
     with pytest.raises(ValueError, match='dest. mesh descriptor and remapping dest.'):
         r4.remap_numpy(da)
-    for method in (r.build_map, r.ncremap):
-        with pytest.raises(NotImplementedError):
-            method()
+    with pytest.raises(NotImplementedError):
+        r.build_map()
 
 
 def test_load_mapping_builds_canonical_csr_once(tmp_path):
