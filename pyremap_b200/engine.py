@@ -535,6 +535,10 @@ def _apply_host_streamed(matrix, lay, host, threshold, mode, device, kernel, tor
     return arr.reshape(lay.out_shape) if out is None else out
 
 
+#: rows up to this many bytes are packed side by side with other variables' (K-concatenation)
+_THIN_ROW_BYTES = 256
+
+
 def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
                        kernel=KERNEL_AUTO):
     """Remap several host variables through ONE streamed pipeline.
@@ -553,6 +557,7 @@ def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
     device = require_cuda(device)
     results = [None] * len(fields)
     jobs, where = [], []
+    thin = {}            # (branch, dtype) -> [(index, layout, host view)] of K-concatenable variables
     for i, (field, remap_axes) in enumerate(fields):
         lay = Layout(field.shape, remap_axes, dst_dims)
         if lay.n_src != matrix.shape[1]:
@@ -568,14 +573,44 @@ def apply_weights_many(matrix, dst_dims, fields, threshold=None, *, device=None,
                                        device=device, kernel=kernel)
             continue
         mode_code = _host_mode(host, threshold, 'auto')
+        if lay.B == 1 and lay.L * host.element_size() <= _THIN_ROW_BYTES:
+            thin.setdefault((mode_code, host.dtype), []).append((i, lay, host))
+            continue
         out_t, arr, direct = _new_result((lay.B, lay.n_dst, lay.L), np.float64, torch, device.index)
         jobs.append(_Job(lay, host.view(lay.B, lay.n_src, lay.L), mode_code,
                          float(threshold) if threshold is not None else 0.0, False, out_t, direct))
-        where.append((i, arr))
+        where.append((i, arr, None))
+    # K-concatenation: variables with short rows -- 2-D fields such as
+    # (Time=1, nCells), a few levels -- that take the same branch are packed side by side into
+    # ONE [nSrc, sum(L)] job: one launch whose gathers read sum(L) contiguous elements per
+    # source row instead of one launch per variable reading 8 bytes per row.  Every column is
+    # computed exactly as it would be alone (the recurrence is per element).
+    for (mode_code, _), members in thin.items():
+        widths = [lay.L for _, lay, _ in members]
+        if len(members) == 1:
+            i, lay, host = members[0]
+            packed = host.view(1, lay.n_src, lay.L)
+        else:
+            packed = torch.cat([host.view(lay.n_src, lay.L) for _, lay, host in members],
+                               dim=1).view(1, members[0][1].n_src, sum(widths))
+        lay_p = Layout((members[0][1].n_src, sum(widths)), [0], dst_dims)
+        out_t, arr, direct = _new_result((1, lay_p.n_dst, lay_p.L), np.float64, torch, device.index)
+        jobs.append(_Job(lay_p, packed, mode_code,
+                         float(threshold) if threshold is not None else 0.0, False, out_t, direct))
+        where.append((None, arr, members))
     if jobs:
         _stream_jobs(matrix, jobs, device, kernel, torch)
-        for (i, arr), job in zip(where, jobs):
-            results[i] = arr.reshape(job.lay.out_shape)
+        for (i, arr, members), job in zip(where, jobs):
+            if members is None:
+                results[i] = arr.reshape(job.lay.out_shape)
+            elif len(members) == 1:
+                results[members[0][0]] = arr.reshape(members[0][1].out_shape)
+            else:
+                wide = arr.reshape(job.lay.n_dst, job.lay.L)
+                at = 0
+                for j, lay, _ in members:
+                    results[j] = np.ascontiguousarray(wide[:, at:at + lay.L]).reshape(lay.out_shape)
+                    at += lay.L
     return results
 
 
