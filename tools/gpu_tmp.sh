@@ -1,2 +1,7 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "thin or share_one or dataset_level or golden or streamed or partial_cover" 2>&1 | tail -15
+mkdir -p gpurun_out
+{
+timeout 300 python tools/exp_r2.py --dyns 1 --pfs 0,1
+timeout 300 python tools/exp_r2.py --dyns 1 --pfs 1 --mode unmasked
+} > gpurun_out/tmp_exp.log 2>&1
+cat gpurun_out/tmp_exp.log
