@@ -139,6 +139,14 @@ B200REMAP_API int b200remap_host_any_nan(const void *X, int x_dtype, int64_t n, 
 B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
                         int64_t rows, int64_t cols, void *cuda_stream);
 
+/* out (C-contiguous, `shape`) [i0]...[i_{n-1}] = in[sum_d i_d * in_strides[d]]: a general axis
+ * permutation on the device for the layouts the native batched launch does not cover -- remap
+ * axes that are not adjacent (reference remap_numpy.py:236-256 going in, :280-295 coming out).
+ * elem_size 1, 4 or 8 bytes; 1 <= ndim <= 8; strides in elements. */
+B200REMAP_API int b200remap_permute(const void *in, void *out, int elem_size, int ndim,
+                                    const int64_t *shape, const int64_t *in_strides,
+                                    void *cuda_stream);
+
 /* dst[i, :] = src[rows_dev[i], :] for i < n_rows, rows of row_bytes (multiple of 16) bytes;
  * src rows are src_row_bytes apart.  `src` is any device-accessible pointer -- in particular
  * pinned (mapped) host memory, which makes this the host->device transfer of exactly the

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_transpose', 'b200remap_set_tunable', 'b200remap_debug_divide',
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
     'b200remap_spmm_f32out', 'b200remap_coo_to_csr', 'b200remap_host_pack_runs',
-    'b200remap_auto_kernel', 'b200remap_debug_divide_masked',
+    'b200remap_auto_kernel', 'b200remap_debug_divide_masked', 'b200remap_permute',
 )
 
 
@@ -98,6 +98,9 @@ def load_library():
         lib.b200remap_host_pack_runs.argtypes = [vp, vp, vp, vp, vp, i64, i32]
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+        lib.b200remap_permute.argtypes = [vp, vp, i32, i32, ctypes.POINTER(i64),
+                                          ctypes.POINTER(i64), vp]
+        lib.b200remap_permute.restype = i32
         lib.b200remap_set_tunable.argtypes = [i32, i32]
         lib.b200remap_debug_divide.argtypes = [vp, vp, vp, i64, vp]
         lib.b200remap_debug_divide_masked.argtypes = [vp, vp, vp, i64, vp]
@@ -216,6 +219,16 @@ def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0):
     check(load_library().b200remap_transpose(
         ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), int(elem_size),
         int(nbatch), int(rows), int(cols),
+        ctypes.c_void_p(stream) if stream else None))
+
+
+def permute(in_ptr, out_ptr, elem_size, shape, in_strides, stream=0):
+    """``out`` (C-contiguous, ``shape``) <- ``in`` read with ``in_strides`` (elements)."""
+    n = len(shape)
+    arr = ctypes.c_int64 * n
+    check(load_library().b200remap_permute(
+        ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), int(elem_size), n,
+        arr(*[int(v) for v in shape]), arr(*[int(v) for v in in_strides]),
         ctypes.c_void_p(stream) if stream else None))
 
 

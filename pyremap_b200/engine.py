@@ -146,6 +146,19 @@ def _transpose2d(t, nbatch, rows, cols, torch):
     return out
 
 
+def _permuted(t, order, torch):
+    """``t.permute(order)`` materialised C-contiguous by the library's own kernel
+    (``b200remap_permute``) -- uint8, float32 or float64 CUDA tensors."""
+    t = t if t.is_contiguous() else t.contiguous()
+    shape = [t.shape[a] for a in order]
+    strides = [t.stride(a) for a in order]
+    out = torch.empty(shape, dtype=t.dtype, device=t.device)
+    if out.numel():
+        _cabi.permute(t.data_ptr(), out.data_ptr(), t.element_size(), shape, strides,
+                      torch.cuda.current_stream(t.device).cuda_stream)
+    return out
+
+
 def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                   valid=None, mode='auto', device=None, want_keep=False,
                   return_torch=False, kernel=KERNEL_AUTO, out_dtype=None, out=None):
@@ -238,13 +251,12 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                 # source dims last: make the batch the contiguous K axis
                 x3 = _transpose2d(x3, 1, B, lay.n_src, torch).view(1, lay.n_src, B)
                 if v3 is not None:
-                    v3 = v3.view(B, lay.n_src).t().contiguous().view(1, lay.n_src, B)
+                    v3 = _permuted(v3.view(B, lay.n_src), [1, 0], torch).view(1, lay.n_src, B)
                 transposed, B, L = True, 1, lay.B
         else:
             order = lay.remap_axes + lay.extra_axes
-            x3 = x.permute(order).reshape(1, lay.n_src, lay.K).contiguous()
-            v3 = None if v is None else v.permute(order).reshape(
-                1, lay.n_src, lay.K).contiguous()
+            x3 = _permuted(x, order, torch).view(1, lay.n_src, lay.K)
+            v3 = None if v is None else _permuted(v, order, torch).view(1, lay.n_src, lay.K)
             B, L = 1, lay.K
 
         y3 = torch.empty((B, lay.n_dst, L), dtype=torch.float32 if y_f32 else torch.float64,
@@ -267,10 +279,10 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
                 if transposed:
                     t3 = _transpose2d(t3.view(1, lay.n_dst, lay.B), 1, lay.n_dst,
                                       lay.B, torch) if t3.dtype != torch.uint8 else \
-                        t3.view(lay.n_dst, lay.B).t().contiguous()
+                        _permuted(t3.view(lay.n_dst, lay.B), [1, 0], torch)
                 return t3.reshape(lay.out_shape)
             full = t3.reshape(lay.dst_dims + lay.extra_shape)
-            return full.permute(lay.unpermute_axes()).contiguous()
+            return _permuted(full, lay.unpermute_axes(), torch)
 
         out = restore(y3)
         keep = restore(k3).to(torch.bool) if want_keep else None

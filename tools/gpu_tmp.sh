@@ -1,7 +1,2 @@
 #!/bin/bash
-mkdir -p gpurun_out
-{
-timeout 300 python tools/exp_r2.py --dyns 1 --pfs 0,1
-timeout 300 python tools/exp_r2.py --dyns 1 --pfs 1 --mode unmasked
-} > gpurun_out/tmp_exp.log 2>&1
-cat gpurun_out/tmp_exp.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "permute or golden or transpose or c_abi" 2>&1 | tail -5
