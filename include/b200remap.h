@@ -198,6 +198,7 @@ B200REMAP_API int b200remap_debug_divide_masked(const double *a, const double *b
 
 /* tuning knobs for experiments (process-wide; 0 restores the default):
  *   0: LANES_K: target threads per CTA (32..384, default 160); WROW: 3..6 = 4..32 lanes per row
+ *   1: host_pack_runs: 1 = non-temporal stores instead of memcpy
  *   3: cap on the vector width (1, 2, 4)
  *   4: binning segment length in units of 8 rows (read by b200remap_csr_create; default 256)
  *   7: WROW: resident warps per SM (default: occupancy limit, 24)
