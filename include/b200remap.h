@@ -65,12 +65,15 @@ extern "C" {
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
 /* kernel selection (0 = let the library choose: rows of at most 8 entries on average -> WROW,
- * longer rows -> LANES_K; b200remap_auto_kernel reports the choice) */
+ * longer rows -> SELL; b200remap_auto_kernel reports the choice) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 /* 2..6: selectors of experiments (shared-memory staged kernels for long rows, a non-persistent
  * binned kernel, TMA / cp.async staged pipelines, persistent binned CTAs); they lost to
  * LANES_K / WROW on B200 and were removed -- E_INVALID now */
+#define B200REMAP_KERNEL_SELL     8  /* lanes across K on a sliced-ELL (SELL-32) copy of the
+                                        entries: a warp that walks 32 rows reads entry j of all of
+                                        them as one line; built for maps with > 8 entries per row */
 #define B200REMAP_KERNEL_WROW     7  /* warp tiles of the binned view, claimed dynamically in item
                                         order by persistent warps; no CTA barrier              */
 
