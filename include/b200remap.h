@@ -65,7 +65,8 @@ extern "C" {
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
 /* kernel selection (0 = let the library choose: rows of at most 8 entries on average -> WROW,
- * longer rows -> SELL; b200remap_auto_kernel reports the choice) */
+ * or LANES_K for thin fields (<= 32 bytes per row); longer rows -> SELL;
+ * b200remap_auto_kernel reports the choice) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
 /* 2..6: selectors of experiments (shared-memory staged kernels for long rows, a non-persistent
@@ -202,6 +203,7 @@ B200REMAP_API int b200remap_debug_divide_masked(const double *a, const double *b
 /* tuning knobs for experiments (process-wide; 0 restores the default):
  *   0: LANES_K: target threads per CTA (32..384, default 160); WROW: 3..6 = 4..32 lanes per row
  *   1: host_pack_runs: 1 = non-temporal stores instead of memcpy
+ *   2: 1 = b200remap_csr_create builds the sliced-ELL view for every map (default: long rows only)
  *   3: cap on the vector width (1, 2, 4)
  *   4: binning segment length in units of 8 rows (read by b200remap_csr_create; default 256)
  *   7: WROW: resident warps per SM (default: occupancy limit, 24)
