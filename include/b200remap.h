@@ -65,7 +65,8 @@ extern "C" {
                                     valid(x) = explicit byte mask if given, else !isnan(x) */
 
 /* kernel selection (0 = let the library choose: rows of at most 8 entries on average -> WROW,
- * or LANES_K for thin fields (<= 32 bytes per row); longer rows -> SELL;
+ * or LANES_K for thin fields (<= 32 bytes per row) and small launches (< 48 MB of gathers);
+ * longer rows -> SELL;
  * b200remap_auto_kernel reports the choice) */
 #define B200REMAP_KERNEL_AUTO     0
 #define B200REMAP_KERNEL_LANES_K  1  /* lanes across K on the plain CSR, 4-deep gather loop   */
