@@ -333,18 +333,16 @@ def _write(remapper, src, out_filename, plan, results, attrs_of, src_dims, dst_d
                     fill_value_for(data, fillvalues))
             else:
                 raw = np.asarray(src.read(name))
-                data = np.array(raw, dtype=raw.dtype.newbyteorder('='))
-                fill = None
-                for key in ('_FillValue', 'missing_value'):
-                    if key in attrs_of[name] and fill is None:
-                        fill = np.asarray(attrs_of[name][key]).ravel()[0]
-                var_attrs = attrs_of[name]
-                if fill is not None and data.dtype.kind == 'f':
-                    data = np.where(data == data.dtype.type(fill), np.nan, data)
+                if raw.dtype.kind == 'f':
+                    # a declared fill value becomes NaN and is encoded again by the writer's rule
+                    data = decode_missing(raw, attrs_of[name])
                     fill = fill_value_for(data, fillvalues)
                 else:
-                    fill = None if data.dtype.kind == 'f' else fill
-                put(name, data, dims, var_attrs, fill)
+                    data = np.array(raw, dtype=raw.dtype.newbyteorder('='))
+                    declared = attrs_of[name].get('_FillValue')
+                    fill = None if declared is None or data.dtype.kind == 'S' else \
+                        np.asarray(declared).ravel()[0]
+                put(name, data, dims, attrs_of[name], fill)
 
         # global attributes: the input's, plus history / mesh_name as remap_numpy.py:59-67
         for key, value in src.attrs.items():
