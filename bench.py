@@ -687,10 +687,10 @@ def measure_configs(args, torch, device, m3, csr3, info3, ring, peak):
         res[name] = dict({'ms': ms, 'best_ms': best, 'algorithmic_bytes': int(nbytes),
                           'algorithmic_GBps': gbs, 'frac': gbs / peak, 'kernel': kern}, **extra)
 
-    def spmm(csr, x, y, K, nb, mode, n_src, n_dst, y_f32=False):
+    def spmm(csr, x, y, K, nb, mode, n_src, n_dst, y_f32=False, kernel=_cabi.KERNEL_AUTO):
         code = _cabi.F64 if x.dtype == torch.float64 else _cabi.F32
         csr.spmm(x.data_ptr(), code, K, K, nb, n_src * K, y.data_ptr(), K, n_dst * K, mode,
-                 THRESHOLD, stream=st, y_f32=y_f32)
+                 THRESHOLD, stream=st, y_f32=y_f32, kernel=kernel)
 
     K = N_LEVELS
     n_a, n_b = m3.n_a, m3.n_b
@@ -709,6 +709,12 @@ def measure_configs(args, torch, device, m3, csr3, info3, ring, peak):
     entry('C3 masked, float32 in and out, x8', ms, best,
           launch_bytes(info3, K, BATCH, w_in=4, w_out=4), kernel_name(csr3, 'float', mode=2),
           slices_per_launch=BATCH, tolerance='every element = float32(reference float64 result)')
+    ms, best = time_launches(torch, lambda i: spmm(csr3, ring32, y32, K, BATCH, 2, n_a, n_b, y_f32=True,
+                                                   kernel=_cabi.KERNEL_WROW_F32))
+    entry('C3 masked, float32 in and out, float32 arithmetic (opt-in), x8', ms, best,
+          launch_bytes(info3, K, BATCH, w_in=4, w_out=4), 'wrow_kernel<float,VEC=4,MODE=2,F32C>',
+          slices_per_launch=BATCH,
+          tolerance='NaN placement bit-exact (float64 denominator), values within 1e-6 relative')
     del ring32, y32
     if args.mode == 'masked':
         ring.nan_to_num_(nan=1.5)                   # the unmasked (frac_b) branch needs NaN-free data

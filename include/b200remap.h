@@ -76,6 +76,13 @@ extern "C" {
 #define B200REMAP_KERNEL_SELL     8  /* lanes across K on a sliced-ELL (SELL-32) copy of the
                                         entries: a warp that walks 32 rows reads entry j of all of
                                         them as one line; built for maps with > 8 entries per row */
+#define B200REMAP_KERNEL_WROW_F32 9  /* WROW with float32 products and sums, never chosen by AUTO:
+                                        float32 fields and float32 results only
+                                        (b200remap_spmm_f32out, no explicit mask).  The masked
+                                        denominator -- all the keep decision depends on -- stays
+                                        the exact float64 recurrence: NaN / mask placement is
+                                        bit-identical to the reference, values agree within 1e-6
+                                        relative (the north star's bar for float32 fields)      */
 #define B200REMAP_KERNEL_WROW     7  /* warp tiles of the binned view, claimed dynamically in item
                                         order by persistent warps; no CTA barrier              */
 

@@ -15,8 +15,8 @@ import threading
 from . import build as _build
 
 MODE_RAW, MODE_FRACB, MODE_MASKED = 0, 1, 2
-KERNEL_AUTO, KERNEL_LANES_K, KERNEL_WROW, KERNEL_SELL = 0, 1, 7, 8
-KERNEL_NAMES = {1: 'lanes_k_kernel', 7: 'wrow_kernel', 8: 'sell_kernel'}
+KERNEL_AUTO, KERNEL_LANES_K, KERNEL_WROW, KERNEL_SELL, KERNEL_WROW_F32 = 0, 1, 7, 8, 9
+KERNEL_NAMES = {1: 'lanes_k_kernel', 7: 'wrow_kernel', 8: 'sell_kernel', 9: 'wrow_kernel'}
 F64, F32 = 0, 1
 
 #: every symbol ``include/b200remap.h`` declares

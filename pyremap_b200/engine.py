@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _cabi
-from ._cabi import (F32, F64, KERNEL_AUTO, MODE_FRACB, MODE_MASKED, MODE_RAW,
+from ._cabi import (F32, F64, KERNEL_AUTO, KERNEL_WROW_F32, MODE_FRACB, MODE_MASKED, MODE_RAW,
                     B200RemapError)
 
 _MAX_BATCH = 65535

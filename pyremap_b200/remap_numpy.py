@@ -286,7 +286,7 @@ def _remap_numpy_array(remapper, in_field, remap_axes,
 
 
 def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
-                return_torch=False, out_dtype=None, out=None, mode='auto'):
+                return_torch=False, out_dtype=None, out=None, mode='auto', arithmetic=None):
     """NaN-filled remap of a plain array or CUDA tensor (new, not in the
     reference): what ``_remap_data_array`` computes for ``da.values``, i.e.
     ``isnan`` -> mask, ``_remap_numpy_array``, masked -> NaN, in one launch.
@@ -294,7 +294,12 @@ def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
     (the reference always returns float64, which stays the default).
     ``mode='masked'``/``'fracb'`` imposes the branch instead of deriving it from an
     any-NaN scan of ``field`` -- for callers that hold only part of a variable
-    (the reference decides per whole variable, remap_numpy.py:202-204)."""
+    (the reference decides per whole variable, remap_numpy.py:202-204).
+    ``arithmetic='float32'`` (float32 fields with ``out_dtype=np.float32`` only) multiplies and
+    sums in float32 -- values within 1e-6 relative of the reference, NaN placement still
+    bit-exact (the masked denominator stays float64); the default is the exact float64 path."""
+    if arithmetic not in (None, 'float64', 'float32'):
+        raise ValueError("arithmetic must be None, 'float64' or 'float32'")
     if remapper.map_filename is None and remapper._matrix is None:
         raise ValueError('No mapping file has been defined')
     _load_mapping(remapper)
@@ -302,4 +307,5 @@ def remap_array(remapper, field, remap_axes, renormalization_threshold=None,
         remapper._matrix, _dst_dims(remapper), field, list(remap_axes),
         renormalization_threshold, mode=mode,
         device=getattr(remapper, 'device', None), return_torch=return_torch,
-        out_dtype=out_dtype, out=out)
+        out_dtype=out_dtype, out=out,
+        kernel=engine.KERNEL_WROW_F32 if arithmetic == 'float32' else engine.KERNEL_AUTO)

@@ -70,15 +70,18 @@ class Remapper:
     remap = remap_numpy
 
     def remap_array(self, field, remap_axes, renormalization_threshold=None,
-                    return_torch=False, out_dtype=None, out=None, mode='auto'):
+                    return_torch=False, out_dtype=None, out=None, mode='auto', arithmetic=None):
         """Array-level entry: numpy array or CUDA tensor in, NaN-filled float64
         out (``return_torch=True`` keeps the result on the device;
         ``out_dtype=np.float32`` rounds the float64 result to float32 on the GPU;
         ``out=`` a preallocated host result, ideally pinned, for host inputs;
         ``mode='masked'|'fracb'`` imposes the branch the reference would pick for the
-        whole variable when ``field`` is only a part of it)."""
+        whole variable when ``field`` is only a part of it; ``arithmetic='float32'``: float32
+        products and sums for float32 fields with float32 results, within 1e-6 of the
+        reference, NaN placement exact)."""
         return remap_array(self, field, remap_axes, renormalization_threshold,
-                           return_torch=return_torch, out_dtype=out_dtype, out=out, mode=mode)
+                           return_torch=return_torch, out_dtype=out_dtype, out=out, mode=mode,
+                           arithmetic=arithmetic)
 
     # ---- out of scope (CPU, stays with pyremap) -----------------------
     def build_map(self, logger=None):
