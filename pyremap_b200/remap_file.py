@@ -309,7 +309,7 @@ def _write(remapper, src, out_filename, plan, results, attrs_of, src_dims, dst_d
             if fill is not None:
                 setattr(var, '_FillValue', np.asarray(fill, dtype=data.dtype))
             if tuple(dims) == ():
-                var.assignValue(data)
+                var.data[...] = data          # (scipy's assignValue indexes 0-d data with [:])
             else:
                 var[:] = data
             written.append(name)

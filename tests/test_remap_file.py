@@ -179,6 +179,48 @@ def test_remap_file_variable_list_overwrite_and_mpas_fill(tmp_path, monkeypatch)
         assert np.nanmin(nc.variables['temperature'][...]) < -1e30
 
 
+def test_remap_file_classic_format_scalar_and_nonadjacent_dims(tmp_path, monkeypatch):
+    """NetCDF-3 classic input (version 1), a scalar variable, an int variable on the source grid
+    and a variable whose source dims are not adjacent, ``(lat, depth, lon)``: the destination
+    dims take the place of the first source dim (remap_numpy.py:171-182)."""
+    m = syn.make_c1(20.0, 10.0)
+    r = _remapper(tmp_path, m)
+    nlat, nlon = m.src_descriptor.dim_sizes
+    rng = np.random.default_rng(3)
+    odd = rng.normal(size=(nlat, 3, nlon))
+    mask = rng.integers(0, 2, size=(nlat, nlon)).astype(np.int32)
+    src = str(tmp_path / 'in.nc')
+    with netcdf_file(src, 'w', version=1) as nc:
+        nc.createDimension('lat', nlat)
+        nc.createDimension('depth', 3)
+        nc.createDimension('lon', nlon)
+        v = nc.createVariable('odd', 'f8', ('lat', 'depth', 'lon'))
+        v[:] = odd
+        v = nc.createVariable('landmask', 'i4', ('lat', 'lon'))
+        v[:] = mask
+        v = nc.createVariable('year', 'i4', ())
+        v.data[...] = 2001
+    monkeypatch.setattr(engine, 'apply_weights_many', _oracle_many(m))
+    out_path = str(tmp_path / 'out.nc')
+    written = r.remap_file(src, out_path)
+    assert set(written) >= {'odd', 'landmask', 'year'}
+    many = _oracle_many(m)
+    ref_odd, ref_mask = many(None, None, [(odd, [0, 2]), (mask.astype(np.float64), [0, 1])], None)
+    with netcdf_file(out_path, 'r', mmap=False) as nc:
+        v = nc.variables['odd']
+        assert v.dimensions == ('lat', 'lon', 'depth')
+        got = np.array(v[...], dtype=np.float64)
+        assert got.shape == ref_odd.shape
+        ok = ~np.isnan(ref_odd)
+        assert np.array_equal(got[ok].view(np.uint64), ref_odd[ok].view(np.uint64))
+        lm = nc.variables['landmask']
+        assert lm.dimensions == ('lat', 'lon') and lm.data.dtype.kind == 'f'     # float64 result
+        np.testing.assert_array_equal(np.array(lm[...], dtype=np.float64)[~np.isnan(ref_mask)],
+                                      ref_mask[~np.isnan(ref_mask)])
+        assert int(nc.variables['year'].getValue()) == 2001
+        assert 'time' not in nc.dimensions
+
+
 def test_remap_file_preflight_errors(tmp_path):
     m = syn.make_c1(20.0, 10.0)
     src = str(tmp_path / 'in.nc')
