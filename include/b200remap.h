@@ -150,6 +150,13 @@ B200REMAP_API int b200remap_host_any_nan(const void *X, int x_dtype, int64_t n, 
  * used for field-major layouts either side of the product.  elem_size is 4 or 8. */
 B200REMAP_API int b200remap_transpose(const void *in, void *out, int elem_size, int64_t nbatch,
                         int64_t rows, int64_t cols, void *cuda_stream);
+/* the same with leading dimensions: in[b][r][c] at in + (b * rows + r) * ld_in + c, out[b][c][r] at
+ * out + (b * cols + c) * ld_out + r (ld_in >= cols, ld_out >= rows).  Lets the batch axis of a
+ * source-dims-last field, (time, lat, lon), become a K axis padded to a multiple of 4 -- the
+ * 256-bit lanes of the gather (K = 365: 697 -> 392 us on the C2 map) -- without an extra copy. */
+B200REMAP_API int b200remap_transpose_ld(const void *in, void *out, int elem_size, int64_t nbatch,
+                                         int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out,
+                                         void *cuda_stream);
 
 /* out (C-contiguous, `shape`) [i0]...[i_{n-1}] = in[sum_d i_d * in_strides[d]]: a general axis
  * permutation on the device for the layouts the native batched launch does not cover -- remap

@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = (
     'b200remap_host_any_nan', 'b200remap_gather_rows', 'b200remap_copy_runs',
     'b200remap_spmm_f32out', 'b200remap_coo_to_csr', 'b200remap_host_pack_runs',
     'b200remap_auto_kernel', 'b200remap_debug_divide_masked', 'b200remap_permute',
+    'b200remap_transpose_ld',
 )
 
 
@@ -98,6 +99,8 @@ def load_library():
         lib.b200remap_host_pack_runs.argtypes = [vp, vp, vp, vp, vp, i64, i32]
         lib.b200remap_any_nan.argtypes = [vp, i32, i64, vp, vp]
         lib.b200remap_transpose.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+        lib.b200remap_transpose_ld.argtypes = [vp, vp, i32, i64, i64, i64, i64, i64, vp]
+        lib.b200remap_transpose_ld.restype = i32
         lib.b200remap_permute.argtypes = [vp, vp, i32, i32, ctypes.POINTER(i64),
                                           ctypes.POINTER(i64), vp]
         lib.b200remap_permute.restype = i32
@@ -215,10 +218,11 @@ def any_nan(x_ptr, x_dtype, n, flag_ptr, stream=0):
         ctypes.c_void_p(stream) if stream else None))
 
 
-def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0):
-    check(load_library().b200remap_transpose(
+def transpose(in_ptr, out_ptr, elem_size, nbatch, rows, cols, stream=0, ld_in=None, ld_out=None):
+    check(load_library().b200remap_transpose_ld(
         ctypes.c_void_p(in_ptr), ctypes.c_void_p(out_ptr), int(elem_size),
-        int(nbatch), int(rows), int(cols),
+        int(nbatch), int(rows), int(cols), int(cols if ld_in is None else ld_in),
+        int(rows if ld_out is None else ld_out),
         ctypes.c_void_p(stream) if stream else None))
 
 

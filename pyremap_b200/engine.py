@@ -148,8 +148,7 @@ def _transpose2d(t, nbatch, rows, cols, torch):
 
 def _permuted(t, order, torch):
     """``t.permute(order)`` materialised C-contiguous by the library's own kernel
-    (``b200remap_permute``) -- uint8, float32 or float64 CUDA tensors."""
-    t = t if t.is_contiguous() else t.contiguous()
+    (``b200remap_permute``) -- uint8, float32 or float64 CUDA tensors, any strides."""
     shape = [t.shape[a] for a in order]
     strides = [t.stride(a) for a in order]
     out = torch.empty(shape, dtype=t.dtype, device=t.device)
@@ -248,11 +247,20 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
             x3 = x.contiguous().view(B, lay.n_src, L)
             v3 = None if v is None else v.contiguous().view(B, lay.n_src, L)
             if L == 1 and B > 1:
-                # source dims last: make the batch the contiguous K axis
-                x3 = _transpose2d(x3, 1, B, lay.n_src, torch).view(1, lay.n_src, B)
+                # source dims last: make the batch the contiguous K axis -- padded to a multiple
+                # of 4 (zero columns, dropped again on the way back) so that the gathers run in
+                # 256-bit lanes whatever the number of time slices (K = 365: 697 -> 392 us)
+                Kp = lay.B if v3 is not None else (lay.B + 3) // 4 * 4
+                if Kp == lay.B:
+                    x3 = _transpose2d(x3, 1, B, lay.n_src, torch).view(1, lay.n_src, B)
+                else:
+                    xt = torch.zeros((1, lay.n_src, Kp), dtype=x3.dtype, device=device)
+                    _cabi.transpose(x3.data_ptr(), xt.data_ptr(), x3.element_size(), 1, B, lay.n_src,
+                                    stream.cuda_stream, ld_out=Kp)
+                    x3 = xt
                 if v3 is not None:
                     v3 = _permuted(v3.view(B, lay.n_src), [1, 0], torch).view(1, lay.n_src, B)
-                transposed, B, L = True, 1, lay.B
+                transposed, B, L = True, 1, Kp
         else:
             order = lay.remap_axes + lay.extra_axes
             x3 = _permuted(x, order, torch).view(1, lay.n_src, lay.K)
@@ -277,9 +285,14 @@ def apply_weights(matrix, dst_dims, field, remap_axes, threshold=None, *,
         def restore(t3):
             if lay.adjacent:
                 if transposed:
-                    t3 = _transpose2d(t3.view(1, lay.n_dst, lay.B), 1, lay.n_dst,
-                                      lay.B, torch) if t3.dtype != torch.uint8 else \
-                        _permuted(t3.view(lay.n_dst, lay.B), [1, 0], torch)
+                    Kp = t3.shape[-1]            # the padded batch axis (>= lay.B)
+                    if t3.dtype == torch.uint8:
+                        t3 = _permuted(t3.view(lay.n_dst, Kp)[:, :lay.B], [1, 0], torch)
+                    else:
+                        back = torch.empty((lay.B, lay.n_dst), dtype=t3.dtype, device=t3.device)
+                        _cabi.transpose(t3.data_ptr(), back.data_ptr(), t3.element_size(), 1,
+                                        lay.n_dst, lay.B, stream.cuda_stream, ld_in=Kp)
+                        t3 = back
                 return t3.reshape(lay.out_shape)
             full = t3.reshape(lay.dst_dims + lay.extra_shape)
             return _permuted(full, lay.unpermute_axes(), torch)
