@@ -15,8 +15,14 @@
  *                             (mask product, threshold, divide, NaN fill), fused
  *   b200remap_any_nan      <- np.isnan(field) / np.count_nonzero(mask) > 0,
  *                             remap_numpy.py:202-204 (branch selection)
- *   b200remap_transpose    <- in_field.transpose(...).reshape(...) / np.transpose,
+ *   b200remap_transpose, b200remap_transpose_ld, b200remap_permute
+ *                          <- in_field.transpose(...).reshape(...) / np.transpose,
  *                             remap_numpy.py:256 and :295 (layout only)
+ *   b200remap_coo_to_csr   <- csr_matrix((S, (row, col)), shape=(n_b, n_a)) itself,
+ *                             remap_numpy.py:134-137, for large maps
+ *   b200remap_host_any_nan, b200remap_copy_runs, b200remap_host_pack_runs,
+ *   b200remap_gather_rows  <- `field = da.values` reaching the device, remap_numpy.py:201:
+ *                             only the source rows the map touches travel
  *
  * Conventions
  *   - plain C: pointers and sizes only; no exceptions or aborts cross the boundary.
